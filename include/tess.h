@@ -1,0 +1,179 @@
+/* tess.h — C ABI of the B200-native Voronoi cell builder (libtess_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of mcomstock/the-tessellator: per-particle Voronoi cell
+ * construction (uniform-grid binning -> shell-ordered neighbour iteration -> half-space clipping
+ * -> volume / face areas / neighbour list).  The reference has no FFI layer; its boundary is the
+ * Rust API of src/interface.rs.  Each entry point below names the reference item it replaces.
+ * The reference API is per-cell (`Diagram::get_cell_at_index(i).compute_voronoi_cell()`); this
+ * ABI is batch (all cells of a diagram per call) and the per-cell Rust/C++/Python wrappers read
+ * rows of the batch result (INTEGRATION.md shows the Rust-side binding).
+ *
+ * Conventions
+ *   - every function returns 0 (TESS_OK) or a negative tess_error; tess_last_error() gives text
+ *     (thread-local).  No C++ exception crosses this boundary.
+ *   - the library owns all device memory; callers free only through *_destroy / *_free.
+ *   - ids are 64-bit to match Rust `usize`; container-wall faces are reported as neighbour ids
+ *     -1..-6 (y_min, x_max, y_max, x_min, z_max, z_min = the reference's face slots F,R,B,L,U,D,
+ *     polyhedron.rs:74-81) instead of the reference's `unwrap()` panic (polyhedron.rs:877).
+ *   - there is NO CPU fallback: every compute entry point fails with TESS_ERR_CUDA when no
+ *     sm_100 device is usable.
+ *   - `stream` arguments are `cudaStream_t` passed as void* (NULL = the legacy default stream).
+ */
+#ifndef TESS_H_
+#define TESS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tess_diagram tess_diagram; /* interface.rs:25  struct Diagram */
+typedef struct tess_result tess_result;   /* the Vec<..> returns of interface.rs:337-384, batched */
+
+typedef enum tess_error {
+    TESS_OK = 0,
+    TESS_ERR_INVALID = -1,     /* bad argument */
+    TESS_ERR_STATE = -2,       /* call order (e.g. add after initialize; interface.rs:65 debug_assert) */
+    TESS_ERR_CUDA = -3,        /* CUDA runtime failure or no usable device */
+    TESS_ERR_NOMEM = -4,
+    TESS_ERR_UNSUPPORTED = -5, /* e.g. real_type != TESS_F64 in this build */
+    TESS_ERR_CAPACITY = -6     /* a cell exceeded even the large-cell path's tables */
+} tess_error;
+
+/* float.rs:78 — the reference only implements Float64. */
+enum { TESS_F64 = 0, TESS_F32 = 1 };
+
+/* tess_opts.outputs */
+enum {
+    TESS_OUT_VOLUME = 1u << 0,    /* Cell::compute_volume            interface.rs:337 */
+    TESS_OUT_NEIGHBORS = 1u << 1, /* Cell::compute_neighbors         interface.rs:342 */
+    TESS_OUT_AREAS = 1u << 2,     /* VoronoiFace::compute_area       interface.rs:408 */
+    TESS_OUT_VERTICES = 1u << 3,  /* Cell::compute_vertices          interface.rs:368 */
+    TESS_OUT_COUNTERS = 1u << 4   /* work counters */
+};
+
+/* per-cell status word (tess_result_status) */
+enum {
+    TESS_STATUS_OK = 0,
+    TESS_STATUS_DEGENERATE_SKIP = 1u << 0,   /* a plane had vertices outside but no strictly Inside->Outside
+                                                edge and was skipped: the reference's behaviour,
+                                                polyhedron.rs:413-434 */
+    TESS_STATUS_TABLE_EXHAUSTED = 1u << 1,   /* shell table ran out before the termination test fired */
+    TESS_STATUS_CAPACITY_OVERFLOW = 1u << 2, /* vertex/edge/face table overflow (cell left unfinished) */
+    TESS_STATUS_HALO_INSUFFICIENT = 1u << 3, /* slab mode: the search reached a grid plane this rank does not hold */
+    TESS_STATUS_INCONSISTENT = 1u << 4       /* mesh invariant broken by floating-point fuzz */
+};
+
+/* Options of one batch computation = the per-cell arguments of Diagram::get_cell_at_index
+ * (interface.rs:186-192).  Initialise with tess_opts_default(). */
+typedef struct tess_opts {
+    double search_radius;  /* NaN = None: expanding search with the results-preserving 2*r_max
+                              termination.  Otherwise ExpandingSearch::expand_all_in_radius(r)
+                              semantics (celery.rs:1023-1075, compares the squared table key with r). */
+    int64_t target_group;  /* -1 = None; else only particles of this group cut (interface.rs:280-297) */
+    uint32_t outputs;      /* TESS_OUT_* mask */
+    int32_t table_radius;  /* half-width R of the precomputed shell-offset table; 0 = default */
+    void* stream;          /* cudaStream_t */
+} tess_opts;
+
+/* Global grid description for slab-sharded (multi-GPU) diagrams.  Every rank passes the SAME
+ * bounds / n_global so that all ranks bin with identical parameters (celery.rs:81-189). */
+typedef struct tess_slab {
+    double bounds[6];    /* x_min,x_max,y_min,y_max,z_min,z_max of ALL points (celery.rs:117-124) */
+    uint64_t n_global;   /* total number of points: cpd = floor(cbrt(n/1.25))+1 (celery.rs:161-162) */
+    uint32_t own_lo;     /* owned grid x-planes [own_lo, own_hi) : cells of points in these planes are computed */
+    uint32_t own_hi;
+    uint32_t local_lo;   /* x-planes [local_lo, local_hi) held by this rank (owned + halo) */
+    uint32_t local_hi;
+} tess_slab;
+
+const char* tess_last_error(void);
+int tess_version(void);
+/* number of usable sm_100 devices (0 if none); never fails */
+int tess_device_count(void);
+
+void tess_opts_default(tess_opts* o);
+
+/* ---- Diagram (interface.rs:25-233) ------------------------------------------------------- */
+
+/* Diagram::default()  interface.rs:24.  device = CUDA ordinal. */
+int tess_diagram_create(tess_diagram** out, int real_type, int device);
+void tess_diagram_destroy(tess_diagram* d);
+
+/* Diagram::add_particle_with_group x n  (interface.rs:52-57).  Host AoS: point i has its x,y,z
+ * (f64) at xyz + i*stride_bytes (ToCeleryPoint getters, celery.rs:56-60).  groups may be NULL
+ * (all group 0).  May be called repeatedly before initialize. */
+int tess_diagram_add_particles(tess_diagram* d, const void* xyz, size_t n, size_t stride_bytes, const uint64_t* groups, void* stream);
+/* Same, from device memory: packed f64 triples.  ids (device, nullable) are the user-visible
+ * ("original", interface.rs:36) indices reported as neighbours; default = insertion order. */
+int tess_diagram_add_particles_device(tess_diagram* d, const double* xyz_dev, size_t n, const uint64_t* groups_dev, const int64_t* ids_dev, void* stream);
+/* Drop all particles but keep device workspaces (lets a handle be reused step after step). */
+int tess_diagram_clear(tess_diagram* d);
+
+/* Diagram::initialize (interface.rs:60-84): bounds, cell sizing, binning (Celery::reset,
+ * celery.rs:253-266).  box = container x_min,y_min,z_min,x_max,y_max,z_max (the arguments of
+ * Polyhedron::new, polyhedron.rs:226-233); NULL = bounding box of the points. */
+int tess_diagram_initialize(tess_diagram* d, const double box[6], void* stream);
+/* Slab-sharded variant: this rank holds the particles of grid x-planes [local_lo, local_hi) of a
+ * global grid and computes the cells of [own_lo, own_hi).  box must be given. */
+int tess_diagram_initialize_slab(tess_diagram* d, const double box[6], const tess_slab* slab, void* stream);
+
+/* Grid facts (celery.rs:146-148, 213, 117-124), valid after initialize. */
+int tess_diagram_grid_info(const tess_diagram* d, uint64_t* n_points, uint64_t* cells_per_dimension, double bounds[6], double cell_sizes[3], double inverse_cell_sizes[3]);
+/* Copies of Celery::{cells, sorted_indices, delimiters} (celery.rs:198-215) for parity tests.
+ * Any pointer may be NULL.  cells/sorted_indices: n entries; delimiters: local cells + 1. */
+int tess_diagram_copy_grid(const tess_diagram* d, uint64_t* cells, uint64_t* sorted_indices, uint64_t* delimiters);
+/* Bit-exact copy of the truncated, canonically ordered search table (celery.rs:418-679) the
+ * clip kernel walks: keys[len], ijk[3*len].  Pass NULL pointers to query len only. */
+int tess_diagram_copy_search_order(const tess_diagram* d, int32_t table_radius, uint64_t* len, double* keys, int32_t* ijk, int* is_full);
+
+/* ---- Cells (interface.rs:237-417), batched ----------------------------------------------- */
+
+/* For every particle (every owned particle in slab mode):
+ *   Diagram::get_cell_at_index(i, Polyhedron::new(box), search_radius, target_group)
+ *   .compute_voronoi_cell()  + compute_volume / compute_neighbors / compute_faces->compute_area.
+ * Result rows: whole-domain diagrams -> row i is particle i (insertion order); slab diagrams ->
+ * rows follow the rank's grid order and tess_result_cell_ids gives the particle id of each row. */
+int tess_compute_all(const tess_diagram* d, const tess_opts* opts, tess_result** out);
+/* Diagram::get_cell_at_particle (interface.rs:211-232): cells of m arbitrary positions (host,
+ * packed f64 triples) that are not particles of the diagram (no self exclusion). */
+int tess_compute_at_points(const tess_diagram* d, const double* xyz, size_t m, const tess_opts* opts, tess_result** out);
+
+void tess_result_free(tess_result* r);
+int tess_result_n_cells(const tess_result* r, uint64_t* n_cells, uint64_t* n_faces);
+/* Host views (copied from the device on first use, valid until tess_result_free). */
+int tess_result_volumes(tess_result* r, const double** out);         /* n_cells */
+int tess_result_face_offsets(tess_result* r, const uint64_t** out);  /* n_cells+1, CSR */
+int tess_result_neighbors(tess_result* r, const int64_t** out);      /* n_faces; walls -1..-6 */
+int tess_result_areas(tess_result* r, const double** out);           /* n_faces */
+int tess_result_status(tess_result* r, const uint32_t** out);        /* n_cells, TESS_STATUS_* */
+int tess_result_cell_ids(tess_result* r, const int64_t** out);       /* n_cells */
+int tess_result_vertex_offsets(tess_result* r, const uint64_t** out); /* n_cells+1 (TESS_OUT_VERTICES) */
+int tess_result_vertices(tess_result* r, const double** out);         /* xyz triples, cell-local coordinates */
+/* counters[8] = candidates visited, candidates tested, vertex classifications, cuts,
+ * new vertices, table entries consumed, degenerate skips, faces */
+int tess_result_counters(tess_result* r, uint64_t counters[8]);
+/* Sum of all volumes computed on the device (closure check: equals the container volume). */
+int tess_result_volume_sum(tess_result* r, double* out);
+/* Device views for callers that keep results on the GPU (any pointer may be NULL). */
+int tess_result_device_views(const tess_result* r, const double** volumes, const uint64_t** face_offsets, const int64_t** neighbors, const double** areas, const uint32_t** status, const int64_t** cell_ids);
+
+/* ---- Slab partition helpers (multi-GPU; the collectives themselves are the caller's) ------ */
+
+/* Histogram of particles per global grid x-plane: counts_dev[cpd] (u64, device, zeroed by the call). */
+int tess_plane_histogram(const double* xyz_dev, size_t n, const double bounds[6], uint64_t n_global, uint64_t* counts_dev, void* stream);
+/* min/max of packed xyz on the device -> bounds_dev[6] (x_min,x_max,y_min,y_max,z_min,z_max). */
+int tess_bounds(const double* xyz_dev, size_t n, double* bounds_dev, void* stream);
+/* Route particles to slabs.  plane_lo/plane_hi[g] (host, n_ranks entries) give for destination
+ * rank g the x-plane range it must RECEIVE (owned + halo).  A particle is sent to every rank whose
+ * range contains its plane.  Outputs (device): send_counts_dev[n_ranks] (u64), and, packed rank
+ * after rank, out_xyz_dev / out_ids_dev (capacity `cap` particles).  ids_dev = ids of the inputs
+ * (NULL -> id_base + i).  Returns TESS_ERR_NOMEM if cap is too small (send_counts_dev still valid). */
+int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t id_base, size_t n, const double bounds[6], uint64_t n_global, int n_ranks, const uint32_t* plane_lo, const uint32_t* plane_hi, uint64_t* send_counts_dev, double* out_xyz_dev, int64_t* out_ids_dev, size_t cap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TESS_H_ */

@@ -1,0 +1,848 @@
+// capi.cu — implementation of include/tess.h: host-side orchestration of the binning pass
+// (grid.cu), the clip kernel (clip.cu) and the CSR outputs (outputs.cu).
+//
+// Host responsibilities that mirror reference code:
+//   * CeleryCellInfo::new (celery.rs:153-189): cpd = floor(cbrt(N/1.25)) + 1 with *glibc* cbrt
+//     (N/1.25 is an exact cube for N = 10k and 10M; a 1-ulp error would change cpd), cell sizes
+//     and inverse sizes with the reference's two divisions;
+//   * Celery::get_search_order (celery.rs:418-679): the offset table, here truncated to
+//     |i|,|j|,|k| <= R and to keys strictly below min_axis sq(R*size) so that it is an exact
+//     prefix of the reference's full (2cpd-1)^3 table, ordered canonically by (key, i, j, k).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tess.h"
+#include "common.cuh"
+
+using namespace tess;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+struct DevBuf {  // grow-only device buffer
+    void* p = nullptr;
+    size_t bytes = 0;
+    void reserve(size_t need) {
+        if (need <= bytes) return;
+        if (p) TESS_CUDA_CHECK(cudaFree(p));
+        p = nullptr;
+        bytes = 0;
+        const size_t want = need + need / 8;
+        TESS_CUDA_CHECK(cudaMalloc(&p, want));
+        bytes = want;
+    }
+    void grow_keep(size_t need, size_t keep_bytes, cudaStream_t s) {  // reserve preserving contents
+        if (need <= bytes) return;
+        void* q = nullptr;
+        const size_t want = std::max(need + need / 2, (size_t)1 << 20);
+        TESS_CUDA_CHECK(cudaMalloc(&q, want));
+        if (p && keep_bytes) TESS_CUDA_CHECK(cudaMemcpyAsync(q, p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+        if (p) {
+            TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+            TESS_CUDA_CHECK(cudaFree(p));
+        }
+        p = q;
+        bytes = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+struct ShellTable {
+    DevBuf dev;
+    uint32_t len = 0;
+    bool full = false;
+    std::vector<ShellEntry> host;
+};
+
+/// float.rs:138-142: `as usize` saturates
+size_t to_usize(double v) {
+    if (!(v > 0.0)) return 0;
+    if (v >= 18446744073709551616.0) return std::numeric_limits<size_t>::max();
+    return static_cast<size_t>(v);
+}
+
+/// CeleryCellInfo::new (celery.rs:153-181)
+void fill_cell_info(GridSpec& g, uint64_t n_points) {
+    const double num_points = static_cast<double>(n_points);
+    const size_t cpd = to_usize(std::cbrt(num_points / 1.25)) + 1;  // celery.rs:161-162, glibc cbrt
+    const double c = static_cast<double>(cpd);
+    g.cpd = static_cast<uint32_t>(cpd);
+    g.sx = (g.xmax - g.xmin) / c;
+    g.sy = (g.ymax - g.ymin) / c;
+    g.sz = (g.zmax - g.zmin) / c;
+    g.ix = c / (g.xmax - g.xmin);
+    g.iy = c / (g.ymax - g.ymin);
+    g.iz = c / (g.zmax - g.zmin);
+}
+
+/// Celery::get_search_order (celery.rs:418-679), truncated to half-width R.
+void build_shell_table(const GridSpec& g, int R, std::vector<ShellEntry>& out, bool& full) {
+    const int max_index = static_cast<int>(g.cpd) - 1;  // celery.rs:430
+    full = (R <= 0 || R >= max_index);
+    const int lim = full ? max_index : R;
+    auto sq = [](double x) { return x * x; };
+    // celery.rs:423-427; an offset o != 0 carries the distance term of |o|-1 (celery.rs:450-457)
+    auto term = [](int o) { return o == 0 ? 0 : std::abs(o) - 1; };
+    out.clear();
+    out.reserve(static_cast<size_t>(2 * lim + 1) * (2 * lim + 1) * (2 * lim + 1));
+    for (int i = -lim; i <= lim; ++i)
+        for (int j = -lim; j <= lim; ++j)
+            for (int k = -lim; k <= lim; ++k) {
+                ShellEntry e;
+                e.di = static_cast<int16_t>(i);
+                e.dj = static_cast<int16_t>(j);
+                e.dk = static_cast<int16_t>(k);
+                e.pad = 0;
+                if (i == 0 && j == 0 && k == 0) {
+                    e.key = -1.0;  // celery.rs:437-442
+                } else {
+                    e.key = sq(static_cast<double>(term(i)) * g.sx) + sq(static_cast<double>(term(j)) * g.sy) + sq(static_cast<double>(term(k)) * g.sz);
+                }
+                out.push_back(e);
+            }
+    // celery.rs:676 sorts by distance only (unstable); the canonical tie-break is (i, j, k)
+    std::sort(out.begin(), out.end(), [](const ShellEntry& a, const ShellEntry& b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.di != b.di) return a.di < b.di;
+        if (a.dj != b.dj) return a.dj < b.dj;
+        return a.dk < b.dk;
+    });
+    if (!full) {
+        const double bound = std::min(sq(static_cast<double>(lim) * g.sx), std::min(sq(static_cast<double>(lim) * g.sy), sq(static_cast<double>(lim) * g.sz)));
+        size_t keep = 0;
+        while (keep < out.size() && out[keep].key < bound) ++keep;
+        out.resize(keep);
+    }
+}
+
+constexpr int kDefaultTableRadius = 8;
+
+}  // namespace
+
+struct tess_diagram {
+    int device = 0;
+    bool initialized = false;
+    bool slab = false;
+    // accumulated input
+    DevBuf xyz, groups, ids;
+    size_t n = 0;
+    bool has_groups = false, has_ids = false;
+    // grid
+    GridSpec grid{};
+    double box[6] = {0, 0, 0, 0, 0, 0};
+    size_t n_cells_local = 0;
+    DevBuf counts, delim, cell_of, rank_in_cell, tmp_idx, sorted, sorted_idx, slot_of, groups_sorted, scan_tmp, small;
+    uint32_t own_slot_begin = 0, own_slot_end = 0;
+    mutable std::mutex mu;
+    mutable std::map<int, ShellTable> tables;
+
+    const ShellTable& table(int R, cudaStream_t s) const {
+        std::lock_guard<std::mutex> lk(mu);
+        int key = R;
+        if (R <= 0 || R >= static_cast<int>(grid.cpd) - 1) key = 0;  // full
+        auto it = tables.find(key);
+        if (it != tables.end()) return it->second;
+        ShellTable& t = tables[key];
+        build_shell_table(grid, key, t.host, t.full);
+        t.len = static_cast<uint32_t>(t.host.size());
+        t.dev.reserve(sizeof(ShellEntry) * t.host.size());
+        TESS_CUDA_CHECK(cudaMemcpyAsync(t.dev.p, t.host.data(), sizeof(ShellEntry) * t.host.size(), cudaMemcpyHostToDevice, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        return t;
+    }
+};
+
+struct tess_result {
+    int device = 0;
+    uint64_t n_cells = 0, n_faces = 0, n_vertices = 0;
+    // device arrays (cudaMalloc)
+    double* vol = nullptr;
+    uint32_t* nfaces = nullptr;
+    uint32_t* status = nullptr;
+    int64_t* cell_id = nullptr;
+    uint64_t* offsets = nullptr;
+    int64_t* nbr = nullptr;
+    double* area = nullptr;
+    uint32_t* nverts = nullptr;
+    uint64_t* voffsets = nullptr;
+    double* vtx = nullptr;
+    unsigned long long* counters = nullptr;
+    // host copies
+    std::vector<double> h_vol, h_area, h_vtx;
+    std::vector<uint64_t> h_offsets, h_voffsets;
+    std::vector<int64_t> h_nbr, h_cell_id;
+    std::vector<uint32_t> h_status;
+    bool have_vol = false, have_area = false, have_offsets = false, have_nbr = false, have_ids = false, have_status = false, have_voff = false, have_vtx = false;
+    ~tess_result() {
+        cudaSetDevice(device);
+        for (void* p : {(void*)vol, (void*)nfaces, (void*)status, (void*)cell_id, (void*)offsets, (void*)nbr, (void*)area, (void*)nverts, (void*)voffsets, (void*)vtx, (void*)counters})
+            if (p) cudaFree(p);
+    }
+};
+
+#define TESS_TRY try {
+#define TESS_CATCH                                            \
+    }                                                         \
+    catch (const std::bad_alloc&) { return fail(TESS_ERR_NOMEM, "out of host memory"); } \
+    catch (const std::exception& e) { return fail(TESS_ERR_CUDA, e.what()); }
+
+static GridSpec spec_from_bounds(const double b[6], uint64_t n_global) {
+    GridSpec g{};
+    g.xmin = b[0]; g.xmax = b[1]; g.ymin = b[2]; g.ymax = b[3]; g.zmin = b[4]; g.zmax = b[5];
+    fill_cell_info(g, n_global);
+    g.local_lo = 0; g.local_hi = g.cpd; g.own_lo = 0; g.own_hi = g.cpd;
+    return g;
+}
+
+extern "C" {
+
+const char* tess_last_error(void) { return g_err.c_str(); }
+int tess_version(void) { return 100; }
+
+int tess_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+void tess_opts_default(tess_opts* o) {
+    if (!o) return;
+    o->search_radius = std::numeric_limits<double>::quiet_NaN();
+    o->target_group = -1;
+    o->outputs = TESS_OUT_VOLUME | TESS_OUT_NEIGHBORS | TESS_OUT_AREAS;
+    o->table_radius = 0;
+    o->stream = nullptr;
+}
+
+int tess_diagram_create(tess_diagram** out, int real_type, int device) {
+    if (!out) return fail(TESS_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (real_type != TESS_F64) return fail(TESS_ERR_UNSUPPORTED, "only TESS_F64 is implemented (the reference implements only Float64, float.rs:78)");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TESS_ERR_CUDA, "no CUDA device available: libtess_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(TESS_ERR_INVALID, "bad device ordinal");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) return fail(TESS_ERR_CUDA, "device is not sm_100 (B200); this library contains sm_100a code only");
+    TESS_TRY
+    TESS_CUDA_CHECK(cudaSetDevice(device));
+    // keep stream-ordered allocations cached between steps
+    cudaMemPool_t pool;
+    TESS_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ull;
+    TESS_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    auto* d = new tess_diagram();
+    d->device = device;
+    *out = d;
+    return TESS_OK;
+    TESS_CATCH
+}
+
+void tess_diagram_destroy(tess_diagram* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (DevBuf* b : {&d->xyz, &d->groups, &d->ids, &d->counts, &d->delim, &d->cell_of, &d->rank_in_cell, &d->tmp_idx, &d->sorted, &d->sorted_idx, &d->slot_of,
+                      &d->groups_sorted, &d->scan_tmp, &d->small})
+        b->release();
+    for (auto& kv : d->tables) kv.second.dev.release();
+    delete d;
+}
+
+static int add_common(tess_diagram* d, size_t n, const void* groups_src, const void* ids_src, cudaMemcpyKind kind, cudaStream_t s) {
+    const size_t n0 = d->n;
+    if (groups_src && !d->has_groups && n0) {  // earlier particles default to group 0
+        d->groups.grow_keep(sizeof(uint64_t) * (n0 + n), 0, s);
+        TESS_CUDA_CHECK(cudaMemsetAsync(d->groups.p, 0, sizeof(uint64_t) * n0, s));
+    }
+    if (groups_src || d->has_groups) {
+        d->groups.grow_keep(sizeof(uint64_t) * (n0 + n), d->has_groups ? sizeof(uint64_t) * n0 : 0, s);
+        if (groups_src) TESS_CUDA_CHECK(cudaMemcpyAsync(d->groups.as<uint64_t>() + n0, groups_src, sizeof(uint64_t) * n, kind, s));
+        else TESS_CUDA_CHECK(cudaMemsetAsync(d->groups.as<uint64_t>() + n0, 0, sizeof(uint64_t) * n, s));
+        d->has_groups = true;
+    }
+    if (ids_src) {
+        if (!d->has_ids && n0) return fail(TESS_ERR_INVALID, "ids must be given for all particles or for none");
+        d->ids.grow_keep(sizeof(int64_t) * (n0 + n), sizeof(int64_t) * n0, s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(d->ids.as<int64_t>() + n0, ids_src, sizeof(int64_t) * n, kind, s));
+        d->has_ids = true;
+    } else if (d->has_ids) {
+        return fail(TESS_ERR_INVALID, "ids must be given for all particles or for none");
+    }
+    d->n = n0 + n;
+    return TESS_OK;
+}
+
+int tess_diagram_add_particles(tess_diagram* d, const void* xyz, size_t n, size_t stride_bytes, const uint64_t* groups, void* stream) {
+    if (!d || (!xyz && n)) return fail(TESS_ERR_INVALID, "NULL argument");
+    if (d->initialized) return fail(TESS_ERR_STATE, "particles must be added before initialize (interface.rs:50-51)");
+    if (stride_bytes < 3 * sizeof(double)) return fail(TESS_ERR_INVALID, "stride_bytes must be >= 24");
+    if (d->n + n >= 0xFFFFFFF0ull) return fail(TESS_ERR_INVALID, "more than 2^32 particles on one device");
+    if (!n) return TESS_OK;
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    d->xyz.grow_keep(sizeof(double) * 3 * (d->n + n), sizeof(double) * 3 * d->n, s);
+    double* dst = d->xyz.as<double>() + 3 * d->n;
+    if (stride_bytes == 3 * sizeof(double))
+        TESS_CUDA_CHECK(cudaMemcpyAsync(dst, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, s));
+    else
+        TESS_CUDA_CHECK(cudaMemcpy2DAsync(dst, 3 * sizeof(double), xyz, stride_bytes, 3 * sizeof(double), n, cudaMemcpyHostToDevice, s));
+    return add_common(d, n, groups, nullptr, cudaMemcpyHostToDevice, s);
+    TESS_CATCH
+}
+
+int tess_diagram_add_particles_device(tess_diagram* d, const double* xyz_dev, size_t n, const uint64_t* groups_dev, const int64_t* ids_dev, void* stream) {
+    if (!d || (!xyz_dev && n)) return fail(TESS_ERR_INVALID, "NULL argument");
+    if (d->initialized) return fail(TESS_ERR_STATE, "particles must be added before initialize (interface.rs:50-51)");
+    if (d->n + n >= 0xFFFFFFF0ull) return fail(TESS_ERR_INVALID, "more than 2^32 particles on one device");
+    if (!n) return TESS_OK;
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    d->xyz.grow_keep(sizeof(double) * 3 * (d->n + n), sizeof(double) * 3 * d->n, s);
+    TESS_CUDA_CHECK(cudaMemcpyAsync(d->xyz.as<double>() + 3 * d->n, xyz_dev, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, s));
+    return add_common(d, n, groups_dev, ids_dev, cudaMemcpyDeviceToDevice, s);
+    TESS_CATCH
+}
+
+int tess_diagram_clear(tess_diagram* d) {
+    if (!d) return fail(TESS_ERR_INVALID, "NULL diagram");
+    d->n = 0;
+    d->has_groups = d->has_ids = false;
+    d->initialized = false;
+    d->slab = false;
+    std::lock_guard<std::mutex> lk(d->mu);
+    for (auto& kv : d->tables) kv.second.dev.release();
+    d->tables.clear();
+    return TESS_OK;
+}
+
+static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* slab, cudaStream_t s) {
+    if (d->initialized) return fail(TESS_ERR_STATE, "diagram already initialized (interface.rs:65)");
+    if (d->n == 0) return fail(TESS_ERR_INVALID, "no particles (CeleryBounds::new panics on an empty set, celery.rs:82)");
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    const size_t n = d->n;
+    d->small.reserve(256);
+    double* dev_bounds = d->small.as<double>();             // 6 doubles
+    uint32_t* dev_flag = reinterpret_cast<uint32_t*>(d->small.as<char>() + 64);
+
+    GridSpec g{};
+    if (slab) {
+        g = spec_from_bounds(slab->bounds, slab->n_global);
+        if (!(slab->local_lo <= slab->own_lo && slab->own_lo <= slab->own_hi && slab->own_hi <= slab->local_hi && slab->local_hi <= g.cpd))
+            return fail(TESS_ERR_INVALID, "slab plane ranges must satisfy local_lo <= own_lo <= own_hi <= local_hi <= cpd");
+        g.local_lo = slab->local_lo; g.local_hi = slab->local_hi; g.own_lo = slab->own_lo; g.own_hi = slab->own_hi;
+        d->slab = true;
+    } else {
+        launch_bounds(d->xyz.as<double>(), n, dev_bounds, s);  // K1: CeleryBounds::new
+        double hb[6];
+        TESS_CUDA_CHECK(cudaMemcpyAsync(hb, dev_bounds, sizeof(hb), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        g = spec_from_bounds(hb, n);
+        d->slab = false;
+    }
+    if (box) {
+        std::memcpy(d->box, box, sizeof(d->box));
+    } else {  // interface.rs:69-79: no container given -> bounding box of the points
+        if (slab) return fail(TESS_ERR_INVALID, "slab diagrams need an explicit container box");
+        d->box[0] = g.xmin; d->box[1] = g.ymin; d->box[2] = g.zmin; d->box[3] = g.xmax; d->box[4] = g.ymax; d->box[5] = g.zmax;
+    }
+    const uint64_t planes = g.local_hi - g.local_lo;
+    const uint64_t ncl = planes * g.cpd * g.cpd;
+    if (ncl >= 0xFFFFFFF0ull) return fail(TESS_ERR_INVALID, "local grid has more than 2^32 cells");
+    d->grid = g;
+    d->n_cells_local = static_cast<size_t>(ncl);
+
+    d->counts.reserve(sizeof(uint32_t) * (ncl + 1));
+    d->delim.reserve(sizeof(uint32_t) * (ncl + 1));
+    d->cell_of.reserve(sizeof(uint32_t) * (n + 2));
+    d->rank_in_cell.reserve(sizeof(uint32_t) * (n + 2));
+    d->tmp_idx.reserve(sizeof(uint32_t) * n);
+    d->sorted.reserve(sizeof(Particle) * n);
+    d->sorted_idx.reserve(sizeof(uint32_t) * n);
+    d->slot_of.reserve(sizeof(uint32_t) * n);
+    if (d->has_groups) d->groups_sorted.reserve(sizeof(uint64_t) * n);
+    d->scan_tmp.reserve(scan_tmp_bytes(ncl + 1));
+
+    TESS_CUDA_CHECK(cudaMemsetAsync(d->counts.p, 0, sizeof(uint32_t) * (ncl + 1), s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(dev_flag, 0, sizeof(uint32_t), s));
+    // K2: cell ids + histogram
+    launch_cell_histogram(d->xyz.as<double>(), n, g, d->cell_of.as<uint32_t>(), d->rank_in_cell.as<uint32_t>(), d->counts.as<uint32_t>(), dev_flag, s);
+    if (slab) {
+        uint32_t flag = 0;
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&flag, dev_flag, sizeof(flag), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (flag) return fail(TESS_ERR_INVALID, "a particle lies outside the slab's local x-plane range");
+    }
+    // K3: delimiters = exclusive scan of the counts (celery.rs:372-414); delim[ncl] = n
+    launch_exclusive_scan_u32(d->counts.as<uint32_t>(), d->delim.as<uint32_t>(), ncl + 1, d->scan_tmp.p, d->scan_tmp.bytes, s);
+    // K4: counting-sort scatter, canonical in-cell order, gather of the particle records
+    launch_scatter(d->cell_of.as<uint32_t>(), d->rank_in_cell.as<uint32_t>(), d->delim.as<uint32_t>(), d->tmp_idx.as<uint32_t>(), n, s);
+    launch_rank_fix_gather(d->tmp_idx.as<uint32_t>(), d->cell_of.as<uint32_t>(), d->delim.as<uint32_t>(), d->xyz.as<double>(), d->has_ids ? d->ids.as<int64_t>() : nullptr,
+                           d->has_groups ? d->groups.as<uint64_t>() : nullptr, d->sorted.as<Particle>(), d->sorted_idx.as<uint32_t>(), d->slot_of.as<uint32_t>(),
+                           d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr, n, s);
+    if (slab) {
+        uint32_t b = 0, e = 0;
+        const size_t cb = static_cast<size_t>(g.own_lo - g.local_lo) * g.cpd * g.cpd, ce = static_cast<size_t>(g.own_hi - g.local_lo) * g.cpd * g.cpd;
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&b, d->delim.as<uint32_t>() + cb, sizeof(b), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&e, d->delim.as<uint32_t>() + ce, sizeof(e), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        d->own_slot_begin = b;
+        d->own_slot_end = e;
+    } else {
+        d->own_slot_begin = 0;
+        d->own_slot_end = static_cast<uint32_t>(n);
+    }
+    {
+        std::lock_guard<std::mutex> lk(d->mu);
+        for (auto& kv : d->tables) kv.second.dev.release();
+        d->tables.clear();
+    }
+    d->initialized = true;
+    return TESS_OK;
+}
+
+int tess_diagram_initialize(tess_diagram* d, const double box[6], void* stream) {
+    if (!d) return fail(TESS_ERR_INVALID, "NULL diagram");
+    TESS_TRY
+    return initialize_impl(d, box, nullptr, static_cast<cudaStream_t>(stream));
+    TESS_CATCH
+}
+
+int tess_diagram_initialize_slab(tess_diagram* d, const double box[6], const tess_slab* slab, void* stream) {
+    if (!d || !slab || !box) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    return initialize_impl(d, box, slab, static_cast<cudaStream_t>(stream));
+    TESS_CATCH
+}
+
+int tess_diagram_grid_info(const tess_diagram* d, uint64_t* n_points, uint64_t* cpd, double bounds[6], double cell_sizes[3], double inverse_cell_sizes[3]) {
+    if (!d) return fail(TESS_ERR_INVALID, "NULL diagram");
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    const GridSpec& g = d->grid;
+    if (n_points) *n_points = d->n;
+    if (cpd) *cpd = g.cpd;
+    if (bounds) { bounds[0] = g.xmin; bounds[1] = g.xmax; bounds[2] = g.ymin; bounds[3] = g.ymax; bounds[4] = g.zmin; bounds[5] = g.zmax; }
+    if (cell_sizes) { cell_sizes[0] = g.sx; cell_sizes[1] = g.sy; cell_sizes[2] = g.sz; }
+    if (inverse_cell_sizes) { inverse_cell_sizes[0] = g.ix; inverse_cell_sizes[1] = g.iy; inverse_cell_sizes[2] = g.iz; }
+    return TESS_OK;
+}
+
+int tess_diagram_copy_grid(const tess_diagram* d, uint64_t* cells, uint64_t* sorted_indices, uint64_t* delimiters) {
+    if (!d) return fail(TESS_ERR_INVALID, "NULL diagram");
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    TESS_TRY
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    TESS_CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<uint32_t> tmp;
+    auto fetch = [&](const DevBuf& b, size_t count, uint64_t* out) {
+        tmp.resize(count);
+        TESS_CUDA_CHECK(cudaMemcpy(tmp.data(), b.p, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < count; ++i) out[i] = tmp[i];
+    };
+    if (cells) fetch(d->cell_of, d->n, cells);
+    if (sorted_indices) fetch(d->sorted_idx, d->n, sorted_indices);
+    if (delimiters) fetch(d->delim, d->n_cells_local + 1, delimiters);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_diagram_copy_search_order(const tess_diagram* d, int32_t table_radius, uint64_t* len, double* keys, int32_t* ijk, int* is_full) {
+    if (!d) return fail(TESS_ERR_INVALID, "NULL diagram");
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    TESS_TRY
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    const ShellTable& t = d->table(table_radius == 0 ? kDefaultTableRadius : table_radius, nullptr);
+    if (len) *len = t.len;
+    if (is_full) *is_full = t.full ? 1 : 0;
+    if (keys && ijk) {
+        // read the table back from the DEVICE copy the kernel walks
+        std::vector<ShellEntry> h(t.len);
+        TESS_CUDA_CHECK(cudaMemcpy(h.data(), t.dev.p, sizeof(ShellEntry) * t.len, cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < t.len; ++i) {
+            keys[i] = h[i].key;
+            ijk[3 * i] = h[i].di; ijk[3 * i + 1] = h[i].dj; ijk[3 * i + 2] = h[i].dk;
+        }
+    }
+    return TESS_OK;
+    TESS_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+template <class T>
+T* dmalloc(size_t count) {
+    void* p = nullptr;
+    TESS_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T)));
+    return static_cast<T*>(p);
+}
+
+struct Scratch {  // stream-ordered temporaries
+    cudaStream_t s;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s_) : s(s_) {}
+    template <class T>
+    T* get(size_t count) {
+        void* p = nullptr;
+        TESS_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(1, count) * sizeof(T), s));
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, s);
+    }
+};
+
+int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* query_host, size_t n_query, tess_result** out) {
+    tess_opts o;
+    if (opts_in) o = *opts_in; else tess_opts_default(&o);
+    cudaStream_t s = static_cast<cudaStream_t>(o.stream);
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    if (o.target_group >= 0 && !d->has_groups && o.target_group != 0) {
+        // every particle is in group 0: nothing can cut
+    }
+    const bool query = query_host != nullptr;
+    const size_t n_rows = query ? n_query : static_cast<size_t>(d->own_slot_end - d->own_slot_begin);
+    const int R0 = o.table_radius > 0 ? o.table_radius : kDefaultTableRadius;
+    const bool want_area = (o.outputs & TESS_OUT_AREAS) != 0;
+    const bool want_vtx = (o.outputs & TESS_OUT_VERTICES) != 0;
+    const bool want_cnt = (o.outputs & TESS_OUT_COUNTERS) != 0;
+
+    std::unique_ptr<tess_result> r(new tess_result());
+    r->device = d->device;
+    r->n_cells = n_rows;
+    r->vol = dmalloc<double>(n_rows);
+    r->nfaces = dmalloc<uint32_t>(n_rows + 1);
+    r->status = dmalloc<uint32_t>(n_rows);
+    r->cell_id = dmalloc<int64_t>(n_rows);
+    r->offsets = dmalloc<uint64_t>(n_rows + 1);
+    r->counters = dmalloc<unsigned long long>(CNT_N);
+    TESS_CUDA_CHECK(cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_N, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(r->nfaces, 0, sizeof(uint32_t) * (n_rows + 1), s));
+    if (want_vtx) {
+        r->nverts = dmalloc<uint32_t>(n_rows + 1);
+        r->voffsets = dmalloc<uint64_t>(n_rows + 1);
+        TESS_CUDA_CHECK(cudaMemsetAsync(r->nverts, 0, sizeof(uint32_t) * (n_rows + 1), s));
+    }
+    if (n_rows == 0) {
+        TESS_CUDA_CHECK(cudaMemsetAsync(r->offsets, 0, sizeof(uint64_t), s));
+        if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(r->voffsets, 0, sizeof(uint64_t), s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        *out = r.release();
+        return TESS_OK;
+    }
+
+    Scratch tmp(s);
+    const uint32_t fstride = 40;  // output capacity of the small path; larger cells go to the large path
+    const uint32_t vstride = clip_small_vmax();
+    int64_t* st_nbr = tmp.get<int64_t>(n_rows * fstride);
+    double* st_area = want_area ? tmp.get<double>(n_rows * fstride) : nullptr;
+    double* st_vtx = want_vtx ? tmp.get<double>(n_rows * (size_t)vstride * 3) : nullptr;
+    uint32_t* ctrl = tmp.get<uint32_t>(8);  // [0] work counter, [1] n_failed, [2] n_failed (large pass)
+    uint32_t* failed = tmp.get<uint32_t>(n_rows);
+    double* query_dev = nullptr;
+    if (query) {
+        query_dev = tmp.get<double>(3 * n_query);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(query_dev, query_host, sizeof(double) * 3 * n_query, cudaMemcpyHostToDevice, s));
+    }
+    void* scan_tmp = tmp.get<char>(scan_tmp_bytes(n_rows + 1));
+    TESS_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 8, s));
+
+    const ShellTable& tab = d->table(R0, s);
+    ClipParams P{};
+    P.sorted = d->sorted.as<Particle>();
+    P.delim = d->delim.as<uint32_t>();
+    P.groups_sorted = d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr;
+    P.table = tab.dev.as<ShellEntry>();
+    P.table_len = tab.len;
+    P.table_full = tab.full ? 1u : 0u;
+    P.grid = d->grid;
+    std::memcpy(P.box, d->box, sizeof(P.box));
+    P.slot_begin = d->own_slot_begin;
+    P.n_work = static_cast<uint32_t>(n_rows);
+    P.work_slots = nullptr;
+    P.query_xyz = query_dev;
+    P.target_group = o.target_group;
+    if (o.target_group >= 0 && !d->has_groups) P.target_group = (o.target_group == 0) ? -1 : -2;  // -2: nothing matches
+    P.search_radius = o.search_radius;
+    P.row_of_slot = (d->slab || query) ? nullptr : d->sorted_idx.as<uint32_t>();
+    P.row_base = d->own_slot_begin;
+    P.vol = r->vol; P.nfaces = r->nfaces; P.status = r->status; P.cell_id = r->cell_id;
+    P.st_nbr = st_nbr; P.st_area = st_area; P.fstride = fstride; P.stage_by_work = 0;
+    P.st_vtx = st_vtx; P.nverts = r->nverts; P.vstride = vstride;
+    P.counters = want_cnt ? r->counters : nullptr;
+    P.work_counter = ctrl;
+    P.failed_slots = query ? nullptr : failed;
+    P.n_failed = ctrl + 1;
+    P.failed_cap = static_cast<uint32_t>(n_rows);
+    P.mark_large = 0;
+    launch_clip(P, /*large=*/false, s);
+
+    // CSR offsets; one sync fetches {n_failed, total}
+    launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
+    uint32_t n_failed = 0;
+    uint64_t total = 0;
+    TESS_CUDA_CHECK(cudaMemcpyAsync(&n_failed, ctrl + 1, sizeof(n_failed), cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+
+    // ---- redo pass: cells the small tables / the default shell table could not finish ----------
+    uint32_t n_redo = 0;
+    int64_t* lg_nbr = nullptr;
+    double* lg_area = nullptr;
+    const uint32_t lstride = clip_large_fmax();
+    if (n_failed > 0) {
+        if (n_failed > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
+        n_redo = n_failed;
+        lg_nbr = tmp.get<int64_t>((size_t)n_redo * lstride);
+        lg_area = want_area ? tmp.get<double>((size_t)n_redo * lstride) : nullptr;
+        uint32_t* failed2 = tmp.get<uint32_t>(n_redo);
+        int R = R0;
+        const int cpd_m1 = static_cast<int>(d->grid.cpd) - 1;
+        for (int attempt = 0; attempt < 12; ++attempt) {
+            R = std::min(std::max(2 * R, 16), std::max(cpd_m1, 1));
+            const ShellTable& t2 = d->table(R, s);
+            ClipParams Q = P;
+            Q.table = t2.dev.as<ShellEntry>();
+            Q.table_len = t2.len;
+            Q.table_full = t2.full ? 1u : 0u;
+            Q.n_work = n_redo;
+            Q.work_slots = failed;
+            Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.fstride = lstride; Q.stage_by_work = 1;
+            Q.st_vtx = nullptr;  // vertices of large cells are not staged (TESS_OUT_VERTICES covers small cells only)
+            Q.counters = nullptr;
+            Q.failed_slots = failed2;
+            Q.n_failed = ctrl + 2;
+            Q.failed_cap = n_redo;
+            Q.mark_large = 1;
+            TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 2, 0, sizeof(uint32_t), s));
+            launch_clip(Q, /*large=*/true, s);
+            uint32_t still = 0;
+            TESS_CUDA_CHECK(cudaMemcpyAsync(&still, ctrl + 2, sizeof(still), cudaMemcpyDeviceToHost, s));
+            TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (still == 0 || t2.full) break;  // remaining failures (if any) are capacity overflows: reported in status
+        }
+        launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+
+    r->n_faces = total;
+    r->nbr = dmalloc<int64_t>(total);
+    if (want_area) r->area = dmalloc<double>(total);
+    launch_compact_faces(r->status, r->offsets, st_nbr, st_area, fstride, n_rows, r->nbr, r->area, s);
+    if (n_redo)
+        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lstride, n_redo, r->nbr, r->area, s);
+    if (want_vtx) {
+        launch_exclusive_scan_u32_to_u64(r->nverts, r->voffsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
+        uint64_t tv = 0;
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&tv, r->voffsets + n_rows, sizeof(tv), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        r->n_vertices = tv;
+        r->vtx = dmalloc<double>(3 * tv);
+        launch_compact_vertices(r->nverts, r->voffsets, st_vtx, vstride, n_rows, r->vtx, s);
+    }
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    *out = r.release();
+    return TESS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tess_compute_all(const tess_diagram* d, const tess_opts* opts, tess_result** out) {
+    if (!d || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    TESS_TRY
+    return compute_impl(d, opts, nullptr, 0, out);
+    TESS_CATCH
+}
+
+int tess_compute_at_points(const tess_diagram* d, const double* xyz, size_t m, const tess_opts* opts, tess_result** out) {
+    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "tess_compute_at_points needs a whole-domain diagram");
+    static const double dummy[3] = {0, 0, 0};
+    TESS_TRY
+    return compute_impl(d, opts, m ? xyz : dummy, m, out);
+    TESS_CATCH
+}
+
+void tess_result_free(tess_result* r) { delete r; }
+
+int tess_result_n_cells(const tess_result* r, uint64_t* n_cells, uint64_t* n_faces) {
+    if (!r) return fail(TESS_ERR_INVALID, "NULL result");
+    if (n_cells) *n_cells = r->n_cells;
+    if (n_faces) *n_faces = r->n_faces;
+    return TESS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <class T>
+int host_view(tess_result* r, const T* dev, size_t count, std::vector<T>& host, bool& have, const T** out) {
+    if (!r || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    try {
+        if (!have) {
+            cudaSetDevice(r->device);
+            host.resize(count);
+            if (count) {
+                if (!dev) return fail(TESS_ERR_STATE, "this output was not requested in tess_opts.outputs");
+                TESS_CUDA_CHECK(cudaMemcpy(host.data(), dev, sizeof(T) * count, cudaMemcpyDeviceToHost));
+            }
+            have = true;
+        }
+        *out = host.data();
+        return TESS_OK;
+    } catch (const std::bad_alloc&) {
+        return fail(TESS_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(TESS_ERR_CUDA, e.what());
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int tess_result_volumes(tess_result* r, const double** out) { return host_view(r, r ? r->vol : nullptr, r ? r->n_cells : 0, r->h_vol, r->have_vol, out); }
+int tess_result_face_offsets(tess_result* r, const uint64_t** out) { return host_view(r, r ? r->offsets : nullptr, r ? r->n_cells + 1 : 0, r->h_offsets, r->have_offsets, out); }
+int tess_result_neighbors(tess_result* r, const int64_t** out) { return host_view(r, r ? r->nbr : nullptr, r ? r->n_faces : 0, r->h_nbr, r->have_nbr, out); }
+int tess_result_areas(tess_result* r, const double** out) { return host_view(r, r ? r->area : nullptr, r ? r->n_faces : 0, r->h_area, r->have_area, out); }
+int tess_result_cell_ids(tess_result* r, const int64_t** out) { return host_view(r, r ? r->cell_id : nullptr, r ? r->n_cells : 0, r->h_cell_id, r->have_ids, out); }
+int tess_result_vertex_offsets(tess_result* r, const uint64_t** out) { return host_view(r, r ? r->voffsets : nullptr, r ? r->n_cells + 1 : 0, r->h_voffsets, r->have_voff, out); }
+int tess_result_vertices(tess_result* r, const double** out) { return host_view(r, r ? r->vtx : nullptr, r ? 3 * r->n_vertices : 0, r->h_vtx, r->have_vtx, out); }
+
+int tess_result_status(tess_result* r, const uint32_t** out) {
+    const bool first = r && !r->have_status;
+    const int rc = host_view(r, r ? r->status : nullptr, r ? r->n_cells : 0, r->h_status, r->have_status, out);
+    if (rc == TESS_OK && first)
+        for (auto& v : r->h_status) v &= ~ST_LARGE_PATH;  // internal bit
+    return rc;
+}
+
+int tess_result_counters(tess_result* r, uint64_t counters[8]) {
+    if (!r || !counters) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    cudaSetDevice(r->device);
+    unsigned long long h[CNT_N];
+    TESS_CUDA_CHECK(cudaMemcpy(h, r->counters, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) counters[i] = h[i];
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_result_volume_sum(tess_result* r, double* out) {
+    if (!r || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    cudaSetDevice(r->device);
+    double* dsum = dmalloc<double>(1);
+    launch_volume_sum(r->vol, r->n_cells, dsum, nullptr);
+    TESS_CUDA_CHECK(cudaMemcpy(out, dsum, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dsum);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_result_device_views(const tess_result* r, const double** volumes, const uint64_t** face_offsets, const int64_t** neighbors, const double** areas,
+                             const uint32_t** status, const int64_t** cell_ids) {
+    if (!r) return fail(TESS_ERR_INVALID, "NULL result");
+    if (volumes) *volumes = r->vol;
+    if (face_offsets) *face_offsets = r->offsets;
+    if (neighbors) *neighbors = r->nbr;
+    if (areas) *areas = r->area;
+    if (status) *status = r->status;
+    if (cell_ids) *cell_ids = r->cell_id;
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab helpers
+// ------------------------------------------------------------------------------------------------
+int tess_bounds(const double* xyz_dev, size_t n, double* bounds_dev, void* stream) {
+    if (!xyz_dev || !bounds_dev || !n) return fail(TESS_ERR_INVALID, "NULL/empty argument");
+    TESS_TRY
+    launch_bounds(xyz_dev, n, bounds_dev, static_cast<cudaStream_t>(stream));
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_plane_histogram(const double* xyz_dev, size_t n, const double bounds[6], uint64_t n_global, uint64_t* counts_dev, void* stream) {
+    if (!bounds || !counts_dev || (!xyz_dev && n)) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GridSpec g = spec_from_bounds(bounds, n_global);
+    TESS_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * g.cpd, s));
+    launch_plane_histogram(xyz_dev, n, g, reinterpret_cast<unsigned long long*>(counts_dev), s);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t id_base, size_t n, const double bounds[6], uint64_t n_global, int n_ranks,
+                        const uint32_t* plane_lo, const uint32_t* plane_hi, uint64_t* send_counts_dev, double* out_xyz_dev, int64_t* out_ids_dev, size_t cap, void* stream) {
+    if (!bounds || !plane_lo || !plane_hi || !send_counts_dev || n_ranks <= 0 || n_ranks > 1024) return fail(TESS_ERR_INVALID, "bad argument");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GridSpec g = spec_from_bounds(bounds, n_global);
+    Scratch tmp(s);
+    uint32_t* lo = tmp.get<uint32_t>(n_ranks);
+    uint32_t* hi = tmp.get<uint32_t>(n_ranks);
+    unsigned long long* offs = tmp.get<unsigned long long>(n_ranks);
+    unsigned long long* cursors = tmp.get<unsigned long long>(n_ranks);
+    TESS_CUDA_CHECK(cudaMemcpyAsync(lo, plane_lo, sizeof(uint32_t) * n_ranks, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(hi, plane_hi, sizeof(uint32_t) * n_ranks, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(send_counts_dev, 0, sizeof(uint64_t) * n_ranks, s));
+    launch_pack_count(xyz_dev, n, g, n_ranks, lo, hi, reinterpret_cast<unsigned long long*>(send_counts_dev), s);
+    std::vector<unsigned long long> hc(n_ranks), ho(n_ranks);
+    TESS_CUDA_CHECK(cudaMemcpyAsync(hc.data(), send_counts_dev, sizeof(uint64_t) * n_ranks, cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    unsigned long long acc = 0;
+    for (int r = 0; r < n_ranks; ++r) { ho[r] = acc; acc += hc[r]; }
+    if (acc > cap || !out_xyz_dev || !out_ids_dev) return fail(TESS_ERR_NOMEM, "pack buffer too small (send counts are valid)");
+    TESS_CUDA_CHECK(cudaMemcpyAsync(offs, ho.data(), sizeof(unsigned long long) * n_ranks, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * n_ranks, s));
+    launch_pack_scatter(xyz_dev, ids_dev, id_base, n, g, n_ranks, lo, hi, offs, cursors, out_xyz_dev, out_ids_dev, s);
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return TESS_OK;
+    TESS_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,761 @@
+// clip.cu — K5: one warp builds one Voronoi cell.
+//
+// Replaces, per cell:
+//   Cell::compute_voronoi_cell / cut_with_point          interface.rs:257-334
+//   ExpandingSearch::{new, expand_all_*}                  celery.rs:882-1075
+//   Polyhedron::{find_outgoing_edge, cut_with_plane}      polyhedron.rs:396-642
+//   Polyhedron::{weighted_normal, compute_volume, compute_neighbors}   polyhedron.rs:776-881
+//   VoronoiFace::compute_area                             interface.rs:408-410
+//
+// Design:
+//   * the polyhedron is a half-edge mesh held in SHARED MEMORY (fixed-capacity tables with
+//     bitmask allocators) instead of pool.rs's heap pools; one half-edge = one 32-bit word
+//     {next, flip, target, face} of 8-bit slot ids (16-bit ids in the large-cell variant);
+//   * candidates are staged 32 at a time: one lane per search-table entry reads the grid
+//     delimiters, a warp scan flattens the per-cell ranges, then one lane per candidate loads its
+//     32-byte particle record, evaluates |r|^2 and builds its bisector plane in parallel;
+//   * plane-side classification is one lane per vertex + warp ballots; the start edge is found by
+//     a lane-per-half-edge ballot; the boundary walk itself is warp-uniform;
+//   * dead vertices/edges/faces are retired by ballots over the tables (no recursion);
+//   * arithmetic is the reference's, operation for operation (tess_math.cuh), so vertex
+//     coordinates — and therefore every Inside/Incident/Outside decision — are bit-identical to
+//     the CPU oracle's.  Slot numbering differs from pool.rs's LIFO order; that only permutes the
+//     order in which faces are listed.
+//   * NEW vs the reference: the shell walk stops at the first table entry whose key exceeds
+//     4*max|v|^2 and skips candidates with |r|^2 >= 4*max|v|^2.  Such candidates cannot have a
+//     vertex Outside (n.v - |r|/2 <= |v| - |r|/2 <= 0 < tol), i.e. find_outgoing_edge
+//     (polyhedron.rs:399-410) would have returned None for them: results are unchanged.
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "tess_math.cuh"
+
+namespace tess {
+
+namespace {
+
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// Bit masks over table slots.  Small cells keep them in registers, large cells in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int NW>
+struct RegMask {
+    uint32_t w[NW];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[k] = 0u;
+    }
+    __device__ __forceinline__ uint32_t word(int k) const { return w[k]; }
+    __device__ __forceinline__ void set_word(int k, uint32_t v) { w[k] = v; }
+    __device__ __forceinline__ bool test(uint32_t i) const {
+        uint32_t x = w[0];
+#pragma unroll
+        for (int k = 1; k < NW; ++k) x = ((i >> 5) == (uint32_t)k) ? w[k] : x;
+        return (x >> (i & 31u)) & 1u;
+    }
+    __device__ __forceinline__ void set(uint32_t i) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[k] |= ((i >> 5) == (uint32_t)k) ? (1u << (i & 31u)) : 0u;
+    }
+    // lowest clear bit below `limit` (and set it), or -1
+    __device__ __forceinline__ int alloc(int limit) {
+        int slot = -1;
+#pragma unroll
+        for (int k = NW - 1; k >= 0; --k) {
+            const uint32_t fr = ~w[k];
+            if (fr) slot = 32 * k + __ffs(fr) - 1;
+        }
+        if (slot >= limit) slot = -1;
+        if (slot >= 0) set((uint32_t)slot);
+        return slot;
+    }
+};
+
+template <int NW>
+struct SmemMask {
+    uint32_t* w;
+    __device__ __forceinline__ void clear() {
+        for (int k = 0; k < NW; ++k) w[k] = 0u;
+    }
+    __device__ __forceinline__ uint32_t word(int k) const { return w[k]; }
+    __device__ __forceinline__ void set_word(int k, uint32_t v) { w[k] = v; }
+    __device__ __forceinline__ bool test(uint32_t i) const { return (w[i >> 5] >> (i & 31u)) & 1u; }
+    __device__ __forceinline__ void set(uint32_t i) { w[i >> 5] |= 1u << (i & 31u); }
+    __device__ __forceinline__ int alloc(int limit) {
+        for (int k = 0; k < NW; ++k) {
+            const uint32_t fr = ~w[k];
+            if (fr) {
+                const int slot = 32 * k + __ffs(fr) - 1;
+                if (slot >= limit) return -1;
+                w[k] |= 1u << (slot & 31);
+                return slot;
+            }
+        }
+        return -1;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Configurations
+// ---------------------------------------------------------------------------------------------
+struct SmallCfg {
+    static constexpr int VMAX = 64, EMAX = 256, FMAX = 64;
+    static constexpr int E_LIMIT = 255;  // slot 255 is the "none" marker of 8-bit ids
+    static constexpr int WARPS = 4;
+    static constexpr bool REG = true;
+    using Idx = uint8_t;
+    using EdgeWord = uint32_t;
+    static constexpr uint32_t NONE = 0xFFu;
+    static constexpr int SHIFT = 8;
+};
+struct LargeCfg {
+    static constexpr int VMAX = 1024, EMAX = 3072, FMAX = 512;
+    static constexpr int E_LIMIT = 3072;
+    static constexpr int WARPS = 1;
+    static constexpr bool REG = false;
+    using Idx = uint16_t;
+    using EdgeWord = unsigned long long;
+    static constexpr uint32_t NONE = 0xFFFFu;
+    static constexpr int SHIFT = 16;
+};
+
+template <class Cfg>
+struct WarpSmem {
+    double vx[Cfg::VMAX], vy[Cfg::VMAX], vz[Cfg::VMAX];
+    long long fnbr[Cfg::FMAX];
+    typename Cfg::EdgeWord edge[Cfg::EMAX];  // {next, flip, target, face}
+    typename Cfg::Idx fstart[Cfg::FMAX];
+    // masks of the large configuration live here (1-word placeholders otherwise)
+    uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
+        m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
+    uint32_t m_flive[Cfg::REG ? 1 : Cfg::FMAX / 32], m_fkeep[Cfg::REG ? 1 : Cfg::FMAX / 32];
+    uint32_t m_elive[Cfg::REG ? 1 : Cfg::EMAX / 32];
+};
+
+template <class Cfg, int NW>
+using MaskT = typename std::conditional<Cfg::REG, RegMask<NW>, SmemMask<NW>>::type;
+
+template <class Cfg>
+struct Mesh {
+    using Idx = typename Cfg::Idx;
+    using EW = typename Cfg::EdgeWord;
+    static constexpr int NWV = Cfg::VMAX / 32, NWE = Cfg::EMAX / 32, NWF = Cfg::FMAX / 32;
+    static constexpr int SH = Cfg::SHIFT;
+    static constexpr EW FM = (EW)Cfg::NONE;  // field mask
+
+    WarpSmem<Cfg>* sm;
+    MaskT<Cfg, NWV> vlive, vbefore, inside, outside, removed;
+    MaskT<Cfg, NWF> flive, fkeep;
+    MaskT<Cfg, NWE> elive;
+    int lane;
+
+    __device__ __forceinline__ void bind(WarpSmem<Cfg>* s, int lane_) {
+        sm = s;
+        lane = lane_;
+        if constexpr (!Cfg::REG) {
+            vlive.w = s->m_vlive; vbefore.w = s->m_vbefore; inside.w = s->m_inside; outside.w = s->m_outside; removed.w = s->m_removed;
+            flive.w = s->m_flive; fkeep.w = s->m_fkeep; elive.w = s->m_elive;
+        }
+    }
+
+    static __device__ __forceinline__ EW pack(uint32_t next, uint32_t flip, uint32_t tgt, uint32_t face) {
+        return (EW)next | ((EW)flip << SH) | ((EW)tgt << (2 * SH)) | ((EW)face << (3 * SH));
+    }
+    static __device__ __forceinline__ uint32_t e_next(EW w) { return (uint32_t)(w & FM); }
+    static __device__ __forceinline__ uint32_t e_flip(EW w) { return (uint32_t)((w >> SH) & FM); }
+    static __device__ __forceinline__ uint32_t e_tgt(EW w) { return (uint32_t)((w >> (2 * SH)) & FM); }
+    static __device__ __forceinline__ uint32_t e_face(EW w) { return (uint32_t)((w >> (3 * SH)) & FM); }
+    // field: 0 next, 1 flip, 2 target, 3 face
+    __device__ __forceinline__ void set_field(uint32_t e, int field, uint32_t v) { reinterpret_cast<Idx*>(&sm->edge[e])[field] = (Idx)v; }
+
+    // Polyhedron::build_cube (polyhedron.rs:268-392) translated by -p (interface.rs:266).
+    __device__ void build_cube(const double* box, double px, double py, double pz) {
+        vlive.clear(); flive.clear(); elive.clear();
+        __syncwarp();
+        if (lane < 8) {
+            // FDL FDR FUR FUL BDL BDR BUR BUL (polyhedron.rs:288-295); corner + (-p)
+            const bool xh = (lane == 1) | (lane == 2) | (lane == 5) | (lane == 6);
+            const bool yh = lane >= 4;
+            const bool zh = (lane == 2) | (lane == 3) | (lane == 6) | (lane == 7);
+            sm->vx[lane] = addd(xh ? box[3] : box[0], -px);
+            sm->vy[lane] = addd(yh ? box[4] : box[1], -py);
+            sm->vz[lane] = addd(zh ? box[5] : box[2], -pz);
+        }
+        if (lane < 24) {
+            // {flip, target, next} per half-edge, ids of polyhedron.rs:97-199 (DR belongs to face D)
+            const uint32_t T[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x050200u, 0x110205u, 0x030106u, 0x170507u, 0x090604u,
+                                    0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
+                                    0x000211u, 0x040612u, 0x080713u, 0x0c0310u, 0x020015u, 0x0e0416u, 0x0a0517u, 0x060114u};
+            const uint32_t t = T[lane];
+            sm->edge[lane] = pack(t & 0xFFu, (t >> 16) & 0xFFu, (t >> 8) & 0xFFu, (uint32_t)lane >> 2);
+        }
+        if (lane < 6) {
+            sm->fstart[lane] = (Idx)(4 * lane);  // FU RU BU LU UF DF (polyhedron.rs:319-379)
+            sm->fnbr[lane] = -(long long)(lane + 1);
+        }
+        vlive.set_word(0, 0xFFu);
+        flive.set_word(0, 0x3Fu);
+        elive.set_word(0, 0xFFFFFFu);
+        __syncwarp();
+    }
+
+    // max |v|^2 over live vertices (left-associated dot, like Vector3::mag_sq)
+    __device__ double max_radius_sq() const {
+        double m = 0.0;
+#pragma unroll
+        for (int p = 0; p < NWV; ++p) {
+            const uint32_t lw = vlive.word(p);
+            if ((lw >> lane) & 1u) {
+                const int v = 32 * p + lane;
+                const double x = sm->vx[v], y = sm->vy[v], z = sm->vz[v];
+                const double r2 = dot3(x, y, z, x, y, z);
+                m = r2 > m ? r2 : m;
+            }
+        }
+        // non-negative doubles order like their bit patterns
+        const unsigned long long b = (unsigned long long)__double_as_longlong(m);
+        const uint32_t hi = __reduce_max_sync(FULL, (uint32_t)(b >> 32));
+        const uint32_t lo = __reduce_max_sync(FULL, ((uint32_t)(b >> 32) == hi) ? (uint32_t)b : 0u);
+        return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One plane against the mesh: Polyhedron::cut_with_plane (polyhedron.rs:438-642).
+// Returns 0 = no cut, 1 = cut, 2 = skipped (D17), <0 = capacity overflow / inconsistency.
+// ---------------------------------------------------------------------------------------------
+template <class Cfg>
+__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, unsigned long long& cnt_vc, unsigned long long& cnt_nv) {
+    using MeshT = Mesh<Cfg>;
+    using EW = typename Cfg::EdgeWord;
+    WarpSmem<Cfg>* sm = M.sm;
+    const int lane = M.lane;
+
+    // ---- classify every live vertex (find_outgoing_edge's vertex scan, polyhedron.rs:399-405,
+    //      and every later vector_location call of the walk) --------------------------------------
+    uint32_t any_out = 0;
+    uint32_t nlive = 0;
+#pragma unroll
+    for (int p = 0; p < MeshT::NWV; ++p) {
+        const uint32_t lw = M.vlive.word(p);
+        M.vbefore.set_word(p, lw);
+        if (!Cfg::REG && lw == 0u) {
+            M.inside.set_word(p, 0u);
+            M.outside.set_word(p, 0u);
+            continue;
+        }
+        const int v = 32 * p + lane;
+        const bool live = (lw >> lane) & 1u;
+        double sd = 0.0;
+        if (live) sd = signed_distance(pl, sm->vx[v], sm->vy[v], sm->vz[v]);
+        const uint32_t in = __ballot_sync(FULL, live && sd < -TESS_TOL);  // vector3.rs:173
+        const uint32_t out = __ballot_sync(FULL, live && sd > TESS_TOL);  // vector3.rs:171
+        M.inside.set_word(p, in);
+        M.outside.set_word(p, out);
+        any_out |= out;
+        nlive += __popc(lw);
+    }
+    cnt_vc += nlive;
+    if (!any_out) return 0;  // polyhedron.rs:408-410
+
+    // ---- first edge (slot order) with target Inside whose flip's target is Outside; the walk
+    //      starts on the flip (polyhedron.rs:413-432) ---------------------------------------------
+    int first = -1;
+#pragma unroll
+    for (int p = 0; p < MeshT::NWE; ++p) {
+        if (first >= 0) break;
+        const uint32_t lw = M.elive.word(p);
+        if (lw == 0u) continue;
+        bool hit = false;
+        uint32_t fl = 0;
+        if ((lw >> lane) & 1u) {
+            const EW w = sm->edge[32 * p + lane];
+            if (M.inside.test(MeshT::e_tgt(w))) {
+                fl = MeshT::e_flip(w);
+                hit = M.outside.test(MeshT::e_tgt(sm->edge[fl]));
+            }
+        }
+        const uint32_t hm = __ballot_sync(FULL, hit);
+        if (hm) first = (int)__shfl_sync(FULL, fl, __ffs(hm) - 1);
+    }
+    if (first < 0) {  // the reference silently skips this plane
+        status |= ST_DEGENERATE_SKIP;
+        return 2;
+    }
+
+    // ---- the walk (polyhedron.rs:475-623), warp-uniform ---------------------------------------
+    const int cap_first = M.elive.alloc(Cfg::E_LIMIT);
+    const int cap_face = M.flive.alloc(Cfg::FMAX);
+    if (cap_first < 0 || cap_face < 0) return -1;
+    sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (polyhedron.rs:479-482)
+    sm->fstart[cap_face] = (typename Cfg::Idx)cap_first;
+    sm->edge[cap_first] = MeshT::pack(Cfg::NONE, Cfg::NONE, Cfg::NONE, (uint32_t)cap_face);
+
+    M.removed.clear();  // vertices_to_destroy (polyhedron.rs:487)
+    uint32_t out_e = (uint32_t)first;
+    uint32_t prev_int = Cfg::NONE;  // previous_intersection
+    uint32_t cap_prev = (uint32_t)cap_first;
+    int nbridge = 0;
+    int guard = 0;
+    do {
+        const EW w_out = sm->edge[out_e];
+        uint32_t pv = MeshT::e_tgt(w_out);  // previous_vertex_index (:491)
+        M.removed.set(pv);
+        uint32_t cur_e = MeshT::e_next(w_out);  // :506
+        EW w_cur = sm->edge[cur_e];
+        uint32_t cv = MeshT::e_tgt(w_cur);
+        bool need = M.outside.test(pv);  // :519
+        while (!M.inside.test(cv)) {     // :529-544
+            need = true;
+            M.removed.set(cv);
+            pv = cv;
+            cur_e = MeshT::e_next(w_cur);
+            w_cur = sm->edge[cur_e];
+            cv = MeshT::e_tgt(w_cur);
+            if (++guard > Cfg::EMAX) {
+                status |= ST_INCONSISTENT;
+                return -2;
+            }
+        }
+        M.set_field(out_e, 2, prev_int);  // :550
+        if (need) {                       // :552-601
+            const int nv = M.vlive.alloc(Cfg::VMAX);
+            const int br = M.elive.alloc(Cfg::E_LIMIT);
+            if (nv < 0 || br < 0) return -1;
+            Vec3 x;
+            const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
+            if (M.outside.test(pv)) {
+                const Vec3 b = {sm->vx[cv], sm->vy[cv], sm->vz[cv]};
+                x = intersection(pl, a, b);  // :567-572 (a = outside end, b = inside end)
+            } else {
+                x = a;  // previous vertex Incident: plain copy (:555-565)
+            }
+            sm->vx[nv] = x.x;
+            sm->vy[nv] = x.y;
+            sm->vz[nv] = x.z;
+            cnt_nv += 1;
+            const uint32_t f = MeshT::e_face(w_out);
+            sm->fstart[f] = (typename Cfg::Idx)out_e;  // :578-580
+            uint32_t capk;
+            if (nbridge == 0) {
+                capk = (uint32_t)cap_first;
+                M.set_field((uint32_t)cap_first, 1, (uint32_t)br);  // :589
+            } else {
+                // the cap edge paired with this bridge: the reference creates it at the end of the
+                // previous crossing (:592-598) with target = previous intersection
+                const int ce = M.elive.alloc(Cfg::E_LIMIT);
+                if (ce < 0) return -1;
+                capk = (uint32_t)ce;
+                sm->edge[capk] = MeshT::pack(cap_prev, (uint32_t)br, prev_int, (uint32_t)cap_face);
+            }
+            sm->edge[br] = MeshT::pack(cur_e, capk, (uint32_t)nv, f);  // :582-587
+            M.set_field(out_e, 0, (uint32_t)br);                        // :590
+            cap_prev = capk;
+            prev_int = (uint32_t)nv;
+            ++nbridge;
+        }
+        out_e = MeshT::e_flip(w_cur);  // :603-607
+        if (++guard > Cfg::EMAX) {
+            status |= ST_INCONSISTENT;
+            return -2;
+        }
+    } while (out_e != (uint32_t)first);  // :620-622
+
+    // close the loop: first outgoing edge and first cap edge end at the last intersection
+    M.set_field((uint32_t)first, 2, prev_int);
+    M.set_field((uint32_t)cap_first, 2, prev_int);
+    M.set_field((uint32_t)cap_first, 0, cap_prev);
+    __syncwarp();
+
+    // ---- retire what was cut off (clean_up_vertices / clean_up_edges / mark_sweep,
+    //      polyhedron.rs:645-730): vertices reached by the walk plus everything connected to them
+    //      through non-Inside vertices; half-edges with both ends removed; faces left without edges.
+    uint32_t missing = 0;
+#pragma unroll
+    for (int p = 0; p < MeshT::NWV; ++p) missing |= (M.vbefore.word(p) & ~M.inside.word(p) & ~M.removed.word(p));
+    if (missing) {
+        // interior of the cut-off region: grow `removed` along edges between non-Inside vertices
+        bool changed = true;
+        int it = 0;
+        while (changed && it++ < Cfg::VMAX) {
+            changed = false;
+#pragma unroll 1
+            for (int p = 0; p < MeshT::NWE; ++p) {
+                const uint32_t lw = M.elive.word(p);
+                if (lw == 0u) continue;
+                uint32_t add_v = Cfg::NONE;
+                if ((lw >> lane) & 1u) {
+                    const EW w = sm->edge[32 * p + lane];
+                    const uint32_t t = MeshT::e_tgt(w), fl = MeshT::e_flip(w);
+                    if (t != Cfg::NONE && fl != Cfg::NONE) {
+                        const uint32_t s = MeshT::e_tgt(sm->edge[fl]);
+                        if (s != Cfg::NONE && M.removed.test(s) && !M.removed.test(t) && M.vbefore.test(t) && !M.inside.test(t)) add_v = t;
+                    }
+                }
+                uint32_t am = __ballot_sync(FULL, add_v != Cfg::NONE);
+                while (am) {  // rare: serialise
+                    const int l = __ffs(am) - 1;
+                    am &= am - 1;
+                    const uint32_t t = __shfl_sync(FULL, add_v, l);
+                    if (!M.removed.test(t)) {
+                        M.removed.set(t);
+                        changed = true;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < MeshT::NWV; ++p) M.vlive.set_word(p, M.vlive.word(p) & ~M.removed.word(p));
+
+    M.fkeep.clear();
+    if constexpr (!Cfg::REG) __syncwarp();
+    bool inconsistent = false;
+#pragma unroll
+    for (int p = 0; p < MeshT::NWE; ++p) {
+        const uint32_t lw = M.elive.word(p);
+        if (lw == 0u) continue;
+        bool dead = false;
+        uint32_t face = 0;
+        const bool live = (lw >> lane) & 1u;
+        if (live) {
+            const EW w = sm->edge[32 * p + lane];
+            const uint32_t t = MeshT::e_tgt(w);
+            const uint32_t s = MeshT::e_tgt(sm->edge[MeshT::e_flip(w)]);
+            const bool tr = M.removed.test(t), sr = M.removed.test(s);
+            dead = tr && sr;
+            inconsistent |= (tr != sr);
+            face = MeshT::e_face(w);
+        }
+        const uint32_t dm = __ballot_sync(FULL, dead);
+        M.elive.set_word(p, lw & ~dm);
+        const bool keep = live && !dead;  // this half-edge keeps its face alive
+        if constexpr (Cfg::REG) {
+#pragma unroll
+            for (int q = 0; q < MeshT::NWF; ++q) {
+                const uint32_t bits = (keep && (face >> 5) == (uint32_t)q) ? (1u << (face & 31u)) : 0u;
+                M.fkeep.set_word(q, M.fkeep.word(q) | __reduce_or_sync(FULL, bits));
+            }
+        } else {
+            if (keep) atomicOr(&sm->m_fkeep[face >> 5], 1u << (face & 31u));
+        }
+    }
+    __syncwarp();
+    if (__any_sync(FULL, inconsistent)) status |= ST_INCONSISTENT;
+#pragma unroll
+    for (int q = 0; q < MeshT::NWF; ++q) M.flive.set_word(q, M.flive.word(q) & M.fkeep.word(q));
+    __syncwarp();
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel: persistent warps pull cells from a work counter.
+// ---------------------------------------------------------------------------------------------
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams P) {
+    using MeshT = Mesh<Cfg>;
+    using EW = typename Cfg::EdgeWord;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem<Cfg>* sm = reinterpret_cast<WarpSmem<Cfg>*>(smem_raw) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    MeshT M;
+    M.bind(sm, lane);
+
+    const GridSpec& G = P.grid;
+    const int cpd = (int)G.cpd;
+    const bool radius_mode = !(P.search_radius != P.search_radius);  // not NaN
+    unsigned long long c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0, c_deg = 0, c_faces = 0;
+
+    for (;;) {
+        uint32_t work = 0;
+        if (lane == 0) work = atomicAdd(P.work_counter, 1u);
+        work = __shfl_sync(FULL, work, 0);
+        if (work >= P.n_work) break;
+
+        // ---- the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207) -----------
+        double px, py, pz;
+        uint32_t self_slot = 0xFFFFFFFFu;
+        size_t row = work;
+        long long self_id = (long long)work;
+        if (P.query_xyz) {  // get_cell_at_particle (interface.rs:218-231): no self exclusion
+            px = P.query_xyz[3 * (size_t)work];
+            py = P.query_xyz[3 * (size_t)work + 1];
+            pz = P.query_xyz[3 * (size_t)work + 2];
+        } else {
+            self_slot = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
+            const double2* q = reinterpret_cast<const double2*>(P.sorted + self_slot);
+            const double2 a = __ldg(q), b = __ldg(q + 1);
+            px = a.x; py = a.y; pz = b.x;
+            self_id = __double_as_longlong(b.y);
+            row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
+        }
+        const size_t srow = P.stage_by_work ? (size_t)work : row;
+        uint32_t status = 0;
+        M.build_cube(P.box, px, py, pz);
+        double rmax2 = M.max_radius_sq();
+
+        // ExpandingSearch::new (celery.rs:882-902): home cell of the position
+        const int hx = (int)axis_index(px, G.xmin, G.xmax, G.ix, G.cpd);
+        const int hy = (int)axis_index(py, G.ymin, G.ymax, G.iy, G.cpd);
+        const int hz = (int)axis_index(pz, G.zmin, G.zmax, G.iz, G.cpd);
+
+        double stop_thr = radius_mode ? P.search_radius : mul(4.0, rmax2);
+        double rej_thr = radius_mode ? __longlong_as_double(0x7ff0000000000000LL) : stop_thr;
+        bool done = false;
+        bool failed = false;
+
+        for (uint32_t t0 = 0; !done; t0 += 32) {
+            // ---- 32 search_order entries, one per lane (celery.rs:981-1014) -------------------
+            const uint32_t ti = t0 + lane;
+            const bool tvalid = ti < P.table_len;
+            double key = 0.0;
+            uint32_t d0 = 0, cnt = 0;
+            bool marker = false;
+            if (tvalid) {
+                const ShellEntry e = P.table[ti];
+                key = e.key;
+                const int gx = hx + e.di, gy = hy + e.dj, gz = hz + e.dk;
+                if (gx >= 0 && gx < cpd && gy >= 0 && gy < cpd && gz >= 0 && gz < cpd) {
+                    if (gx < (int)G.local_lo || gx >= (int)G.local_hi) {
+                        marker = true;  // a plane this rank does not hold
+                        cnt = 1;
+                    } else {
+                        const uint32_t c = ((uint32_t)(gx - (int)G.local_lo) * G.cpd + (uint32_t)gy) * G.cpd + (uint32_t)gz;
+                        d0 = __ldg(P.delim + c);
+                        cnt = __ldg(P.delim + c + 1) - d0;
+                    }
+                }
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            const uint32_t excl = incl - cnt;
+
+            for (uint32_t base = 0; base < total && !done; base += 32) {
+                // ---- one lane per candidate of the flattened ranges --------------------------
+                const uint32_t q = base + lane;
+                const bool has = q < total;
+                int L = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(FULL, incl, L + step - 1);
+                    if (v <= q) L += step;
+                }
+                L = has ? L : 31;
+                const uint32_t src_d0 = __shfl_sync(FULL, d0, L);
+                const uint32_t src_excl = __shfl_sync(FULL, excl, L);
+                const double src_key = __shfl_sync(FULL, key, L);
+                const bool src_marker = __shfl_sync(FULL, (int)marker, L) != 0;
+                const uint32_t slot = src_d0 + (q - src_excl);
+                double rx = 0, ry = 0, rz = 0, r2 = 0;
+                long long cid = 0;
+                bool adm = false;
+                if (has && !src_marker) {
+                    const double2* cq = reinterpret_cast<const double2*>(P.sorted + slot);
+                    const double2 a = __ldg(cq), b = __ldg(cq + 1);
+                    // interface.rs:322-326: search point - position
+                    rx = subd(a.x, px); ry = subd(a.y, py); rz = subd(b.x, pz);
+                    cid = __double_as_longlong(b.y);
+                    r2 = dot3(rx, ry, rz, rx, ry, rz);
+                    adm = slot != self_slot;  // interface.rs:283/301 (by index)
+                    if (adm && P.target_group != -1)  // interface.rs:284/293 (-2: no particle carries the requested group)
+                        adm = P.target_group >= 0 && P.groups_sorted[slot] == (uint64_t)P.target_group;
+                }
+                uint32_t uncounted = __ballot_sync(FULL, has && !src_marker);  // C_vis bookkeeping
+                // bisector plane of every candidate that can still matter (Plane::halfway_from_origin_to)
+                Plane mypl = {0, 0, 0, 0};
+                const bool cand = (has && src_marker) || (adm && r2 < rej_thr);
+                if (cand && !src_marker) mypl = halfway_from_origin_to(Vec3{rx, ry, rz});
+                uint32_t pending = __ballot_sync(FULL, cand && !(src_key > stop_thr));
+                while (pending) {
+                    const int l = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    if (__shfl_sync(FULL, (int)src_marker, l)) {
+                        status |= ST_HALO_INSUFFICIENT;
+                        continue;
+                    }
+                    Plane pl;
+                    pl.nx = __shfl_sync(FULL, mypl.nx, l);
+                    pl.ny = __shfl_sync(FULL, mypl.ny, l);
+                    pl.nz = __shfl_sync(FULL, mypl.nz, l);
+                    pl.off = __shfl_sync(FULL, mypl.off, l);
+                    const long long nid = __shfl_sync(FULL, cid, l);
+                    c_test += 1;
+                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv);
+                    if (rc < 0) {
+                        if (rc == -1) status |= ST_CAPACITY_OVERFLOW;
+                        failed = true;
+                        done = true;
+                        break;
+                    }
+                    if (rc == 2) c_deg += 1;
+                    if (rc == 1) {
+                        c_cuts += 1;
+                        if (!radius_mode) {
+                            // candidates up to this lane were offered under the old threshold
+                            const uint32_t upto = uncounted & ((2u << l) - 1u);
+                            c_vis += __popc(upto & __ballot_sync(FULL, !(src_key > stop_thr)));
+                            uncounted &= ~upto;
+                            rmax2 = M.max_radius_sq();
+                            stop_thr = mul(4.0, rmax2);
+                            rej_thr = stop_thr;
+                            pending &= __ballot_sync(FULL, cand && !(src_key > stop_thr) && (src_marker || r2 < rej_thr));
+                        }
+                    }
+                }
+                c_vis += __popc(uncounted & __ballot_sync(FULL, !(src_key > stop_thr)));
+                // the walk stops at the first entry whose key exceeds the threshold (celery.rs:1036)
+                if (__ballot_sync(FULL, has && src_key > stop_thr)) done = true;
+            }
+            if (!done) {
+                const uint32_t stopm = __ballot_sync(FULL, tvalid && key > stop_thr);
+                if (stopm) {
+                    done = true;
+                    c_tab += __ffs(stopm) - 1;
+                } else {
+                    c_tab += __popc(__ballot_sync(FULL, tvalid));
+                }
+                if (!done && t0 + 32 >= P.table_len) {
+                    if (!P.table_full && !radius_mode) status |= ST_TABLE_EXHAUSTED;
+                    done = true;
+                }
+            } else if (!failed) {
+                c_tab += __popc(__ballot_sync(FULL, tvalid && !(key > stop_thr)));
+            }
+        }
+
+        // ---- results: weighted normals, areas, volume, neighbours ------------------------------
+        uint32_t nf = 0;
+#pragma unroll
+        for (int q = 0; q < MeshT::NWF; ++q) nf += __popc(M.flive.word(q));
+        double vol_part = 0.0;
+        uint32_t rank_base = 0;
+        if (!failed) {
+#pragma unroll 1
+            for (int q = 0; q < MeshT::NWF; ++q) {
+                const uint32_t lw = M.flive.word(q);
+                if (lw == 0u) continue;
+                if ((lw >> lane) & 1u) {
+                    const int f = 32 * q + lane;
+                    // Polyhedron::weighted_normal (polyhedron.rs:776-808)
+                    const uint32_t s = sm->fstart[f];
+                    EW w = sm->edge[s];
+                    const uint32_t av = MeshT::e_tgt(w);
+                    const Vec3 A = {sm->vx[av], sm->vy[av], sm->vz[av]};
+                    uint32_t e = MeshT::e_next(w);
+                    w = sm->edge[e];
+                    uint32_t tv = MeshT::e_tgt(w);
+                    Vec3 cur = sub(Vec3{sm->vx[tv], sm->vy[tv], sm->vz[tv]}, A);
+                    e = MeshT::e_next(w);
+                    Vec3 wn = {0.0, 0.0, 0.0};
+                    int guard = 0;
+                    while (e != s && guard++ < Cfg::EMAX) {
+                        w = sm->edge[e];
+                        tv = MeshT::e_tgt(w);
+                        const Vec3 prev = cur;
+                        cur = sub(Vec3{sm->vx[tv], sm->vy[tv], sm->vz[tv]}, A);
+                        wn = add(wn, cross(prev, cur));
+                        e = MeshT::e_next(w);
+                    }
+                    const double area = mul(0.5, __dsqrt_rn(dot(wn, wn)));  // interface.rs:408-410
+                    vol_part = addd(vol_part, dot(A, wn));                   // polyhedron.rs:849
+                    const uint32_t rank = rank_base + __popc(lw & ((1u << lane) - 1u));
+                    if (rank < P.fstride) {
+                        P.st_nbr[srow * P.fstride + rank] = sm->fnbr[f];
+                        if (P.st_area) P.st_area[srow * P.fstride + rank] = area;
+                    }
+                }
+                rank_base += __popc(lw);
+            }
+            if (nf > P.fstride) status |= ST_CAPACITY_OVERFLOW;
+        }
+        // volume = (sum over faces) / 6 (polyhedron.rs:854)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vol_part = addd(vol_part, __shfl_xor_sync(FULL, vol_part, o));
+        if (P.st_vtx && !failed) {
+            uint32_t vb = 0;
+#pragma unroll 1
+            for (int p = 0; p < MeshT::NWV; ++p) {
+                const uint32_t lw = M.vlive.word(p);
+                if ((lw >> lane) & 1u) {
+                    const uint32_t r = vb + __popc(lw & ((1u << lane) - 1u));
+                    if (r < P.vstride) {
+                        double* o = P.st_vtx + (srow * P.vstride + r) * 3;
+                        o[0] = sm->vx[32 * p + lane]; o[1] = sm->vy[32 * p + lane]; o[2] = sm->vz[32 * p + lane];
+                    }
+                }
+                vb += __popc(lw);
+            }
+            if (lane == 0) P.nverts[row] = vb < P.vstride ? vb : P.vstride;
+            if (vb > P.vstride) status |= ST_CAPACITY_OVERFLOW;
+        }
+        if (lane == 0) {
+            // cells this configuration cannot finish are queued for the large-cell / larger-table pass
+            const bool bad = (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT | ST_TABLE_EXHAUSTED)) != 0;
+            if (bad && P.failed_slots && !P.query_xyz) {
+                const uint32_t k = atomicAdd(P.n_failed, 1u);
+                if (k < P.failed_cap) P.failed_slots[k] = self_slot;
+            }
+            const bool empty = (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) != 0;
+            P.vol[row] = empty ? 0.0 : __ddiv_rn(vol_part, 6.0);
+            P.nfaces[row] = empty ? 0u : nf;
+            if (P.st_vtx && empty) P.nverts[row] = 0u;
+            P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
+            if (P.cell_id) P.cell_id[row] = self_id;
+        }
+        c_faces += nf;
+        __syncwarp();
+    }
+
+    if (P.counters && lane == 0) {
+        atomicAdd(&P.counters[CNT_VISITED], c_vis);
+        atomicAdd(&P.counters[CNT_TESTED], c_test);
+        atomicAdd(&P.counters[CNT_VC], c_vc);
+        atomicAdd(&P.counters[CNT_CUTS], c_cuts);
+        atomicAdd(&P.counters[CNT_NV], c_nv);
+        atomicAdd(&P.counters[CNT_TABLE], c_tab);
+        atomicAdd(&P.counters[CNT_DEGEN], c_deg);
+        atomicAdd(&P.counters[CNT_FACES], c_faces);
+    }
+}
+
+template <class Cfg>
+void launch_cfg(const ClipParams& p, cudaStream_t s) {
+    if (!p.n_work) return;
+    const size_t smem = sizeof(WarpSmem<Cfg>) * Cfg::WARPS;
+    static bool configured = false;
+    if (!configured) {
+        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int dev = 0, sms = 148, per_sm = 1;
+    TESS_CUDA_CHECK(cudaGetDevice(&dev));
+    TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_kernel<Cfg>, Cfg::WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    // persistent grid: a whole number of resident waves (148 SMs x resident CTAs)
+    const unsigned int want = (unsigned int)((p.n_work + Cfg::WARPS - 1) / Cfg::WARPS);
+    const unsigned int grid = std::min<unsigned int>(want, (unsigned int)(sms * per_sm));
+    TESS_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s));
+    clip_kernel<Cfg><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void launch_clip(const ClipParams& p, bool large, cudaStream_t s) {
+    if (large) launch_cfg<LargeCfg>(p, s);
+    else launch_cfg<SmallCfg>(p, s);
+}
+uint32_t clip_small_fmax() { return SmallCfg::FMAX; }
+uint32_t clip_small_vmax() { return SmallCfg::VMAX; }
+uint32_t clip_large_fmax() { return LargeCfg::FMAX; }
+uint32_t clip_large_vmax() { return LargeCfg::VMAX; }
+
+}  // namespace tess

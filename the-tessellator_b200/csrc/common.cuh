@@ -1,0 +1,118 @@
+// common.cuh — shared host/device structs of libtess_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace tess {
+
+// Uniform grid of celery.rs restricted to the x-planes this rank holds.
+struct GridSpec {
+    double xmin, xmax, ymin, ymax, zmin, zmax;  // CeleryBounds (celery.rs:64-77)
+    double sx, sy, sz;                          // cell sizes (celery.rs:132-136)
+    double ix, iy, iz;                          // inverse cell sizes (celery.rs:140-144)
+    uint32_t cpd;                               // cells_per_dimension (celery.rs:148)
+    uint32_t local_lo, local_hi;                // x-planes present locally
+    uint32_t own_lo, own_hi;                    // x-planes whose cells are computed here
+};
+
+// One entry of the (truncated) search-order table: DistanceIndex of celery.rs:27-32.
+struct ShellEntry {
+    double key;  // squared min cell-to-cell distance; -1 for the home cell
+    int16_t di, dj, dk, pad;
+};
+static_assert(sizeof(ShellEntry) == 16, "ShellEntry is one 16-byte load");
+
+// Sorted particle record: one 32-byte sector per candidate.
+struct __align__(32) Particle {
+    double x, y, z;
+    int64_t id;  // user-visible ("original") index
+};
+
+enum : uint32_t {
+    ST_DEGENERATE_SKIP = 1u << 0,
+    ST_TABLE_EXHAUSTED = 1u << 1,
+    ST_CAPACITY_OVERFLOW = 1u << 2,
+    ST_HALO_INSUFFICIENT = 1u << 3,
+    ST_INCONSISTENT = 1u << 4,
+    ST_LARGE_PATH = 1u << 31,  // internal: the row's faces live in the large-cell staging area
+};
+
+enum : int { CNT_VISITED = 0, CNT_TESTED, CNT_VC, CNT_CUTS, CNT_NV, CNT_TABLE, CNT_DEGEN, CNT_FACES, CNT_N };
+
+struct ClipParams {
+    const Particle* sorted;        // n_local records in grid order
+    const uint32_t* delim;         // local grid cells + 1
+    const uint64_t* groups_sorted; // nullable
+    const ShellEntry* table;
+    uint32_t table_len;
+    uint32_t table_full;           // 1: the table covers the whole grid
+    GridSpec grid;
+    double box[6];                 // container x_min,y_min,z_min,x_max,y_max,z_max
+    // work list: either a contiguous slot range, or an explicit list of slots (redo of flagged cells),
+    // or explicit query positions (get_cell_at_particle)
+    uint32_t slot_begin;
+    uint32_t n_work;
+    const uint32_t* work_slots;    // nullable; work item w -> sorted slot
+    const double* query_xyz;       // nullable; work item w -> position (no self exclusion)
+    int64_t target_group;          // -1 = None
+    double search_radius;          // NaN = None
+    // output row of a cell: row_of_slot[slot] if given, else slot - row_base (query mode: work item)
+    const uint32_t* row_of_slot;
+    uint32_t row_base;
+    // per-row outputs
+    double* vol;
+    uint32_t* nfaces;
+    uint32_t* status;
+    int64_t* cell_id;              // nullable
+    // face staging [rows][fstride]; indexed by row, or by work item when stage_by_work != 0
+    int64_t* st_nbr;
+    double* st_area;
+    uint32_t fstride;
+    uint32_t stage_by_work;
+    // optional vertex staging, same indexing: [..][vstride][3]
+    double* st_vtx;                // nullable
+    uint32_t* nverts;
+    uint32_t vstride;
+    unsigned long long* counters;  // CNT_N, nullable
+    uint32_t* work_counter;        // dynamic work distribution
+    // cells this configuration could not finish (capacity / table exhausted): slots appended here
+    uint32_t* failed_slots;        // nullable
+    uint32_t* n_failed;
+    uint32_t failed_cap;
+    uint32_t mark_large;           // OR ST_LARGE_PATH into the status of every row written
+};
+
+#define TESS_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// kernels' host launchers (grid.cu / clip.cu / outputs.cu)
+void launch_bounds(const double* xyz, size_t n, double* bounds6, cudaStream_t s);
+void launch_cell_histogram(const double* xyz, size_t n, const GridSpec& g, uint32_t* cell_of, uint32_t* rank_in_cell, uint32_t* counts, uint32_t* oob_flag, cudaStream_t s);
+void launch_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* tmp, size_t tmp_bytes, cudaStream_t s);
+size_t scan_tmp_bytes(size_t n);
+void launch_scatter(const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, uint32_t* tmp_idx, size_t n, cudaStream_t s);
+void launch_rank_fix_gather(const uint32_t* tmp_idx, const uint32_t* cell_of, const uint32_t* delim, const double* xyz, const int64_t* ids, const uint64_t* groups, Particle* sorted, uint32_t* sorted_idx, uint32_t* slot_of, uint64_t* groups_sorted, size_t n, cudaStream_t s);
+void launch_plane_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s);
+void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, unsigned long long* counts, cudaStream_t s);
+void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, const unsigned long long* offsets, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, cudaStream_t s);
+
+void launch_clip(const ClipParams& p, bool large, cudaStream_t s);
+uint32_t clip_small_fmax();
+uint32_t clip_small_vmax();
+uint32_t clip_large_fmax();
+uint32_t clip_large_vmax();
+
+void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t n, void* tmp, size_t tmp_bytes, cudaStream_t s);
+void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_rows, int64_t* nbr, double* area, cudaStream_t s);
+void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, cudaStream_t s);
+void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s);
+void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s);
+
+}  // namespace tess

@@ -1,0 +1,126 @@
+// outputs.cu — K6: CSR compaction of the per-cell face lists, and K8: the volume closure sum.
+//
+// The clip kernel leaves each cell's neighbour ids / face areas in a fixed-stride staging row
+// (the batched form of the Vec returns of interface.rs:342-384).  After an exclusive scan of the
+// face counts these kernels pack the rows into CSR arrays with coalesced writes.
+#include "common.cuh"
+
+namespace tess {
+
+namespace {
+
+constexpr int kRowsPerBlock = 256;
+
+// One block packs kRowsPerBlock consecutive rows: every thread walks output positions and finds
+// the owning row by binary search in the block's slice of the offsets.
+__global__ void __launch_bounds__(256) compact_faces_kernel(const uint32_t* __restrict__ status, const uint64_t* __restrict__ offsets,
+                                                            const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area, uint32_t fstride,
+                                                            size_t n_rows, int64_t* __restrict__ nbr, double* __restrict__ area) {
+    __shared__ uint64_t s_off[kRowsPerBlock + 1];
+    const size_t row0 = (size_t)blockIdx.x * kRowsPerBlock;
+    const int rows = (int)min((size_t)kRowsPerBlock, n_rows - row0);
+    for (int i = threadIdx.x; i <= rows; i += blockDim.x) s_off[i] = offsets[row0 + i];
+    __syncthreads();
+    const uint64_t begin = s_off[0], end = s_off[rows];
+    for (uint64_t p = begin + threadIdx.x; p < end; p += blockDim.x) {
+        int lo = 0, hi = rows;  // largest r with s_off[r] <= p
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= p) lo = mid; else hi = mid;
+        }
+        const size_t row = row0 + lo;
+        if (status[row] & ST_LARGE_PATH) continue;  // packed by compact_redo_kernel
+        const uint32_t k = (uint32_t)(p - s_off[lo]);
+        nbr[p] = st_nbr[row * fstride + k];
+        if (area) area[p] = st_area[row * fstride + k];
+    }
+}
+
+// Rows recomputed by the large-cell pass: one warp per work item, staging indexed by work item.
+__global__ void __launch_bounds__(128) compact_redo_kernel(const uint32_t* __restrict__ work_slots, const uint32_t* __restrict__ row_of_slot, uint32_t row_base,
+                                                           const uint32_t* __restrict__ nfaces, const uint64_t* __restrict__ offsets,
+                                                           const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area, uint32_t fstride,
+                                                           size_t n_work, int64_t* __restrict__ nbr, double* __restrict__ area) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_work) return;
+    const uint32_t slot = work_slots[w];
+    const size_t row = row_of_slot ? row_of_slot[slot] : (size_t)(slot - row_base);
+    const uint32_t nf = nfaces[row];
+    const uint64_t o = offsets[row];
+    for (uint32_t k = lane; k < nf; k += 32) {
+        nbr[o + k] = st_nbr[w * fstride + k];
+        if (area) area[o + k] = st_area[w * fstride + k];
+    }
+}
+
+__global__ void __launch_bounds__(256) compact_vertices_kernel(const uint32_t* __restrict__ nverts, const uint64_t* __restrict__ offsets,
+                                                               const double* __restrict__ st_vtx, uint32_t vstride, size_t n_rows, double* __restrict__ vtx) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const uint32_t nv = nverts[w];
+    const uint64_t o = offsets[w];
+    for (uint32_t k = lane; k < 3 * nv; k += 32) vtx[3 * o + k] = st_vtx[w * (size_t)vstride * 3 + k];
+}
+
+// Deterministic two-level sum (fixed block partition, fixed tree) so that repeated runs agree bitwise.
+__global__ void __launch_bounds__(256) volume_partial_kernel(const double* __restrict__ vol, size_t n, double* __restrict__ partial) {
+    __shared__ double s[256];
+    const size_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const size_t b = (size_t)blockIdx.x * per_block;
+    const size_t e = min(n, b + per_block);
+    double acc = 0.0;
+    for (size_t i = b + threadIdx.x; i < e; i += blockDim.x) acc += vol[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void volume_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < nb; ++i) acc += partial[i];
+        *out = acc;
+    }
+}
+
+}  // namespace
+
+void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_rows, int64_t* nbr,
+                          double* area, cudaStream_t s) {
+    if (!n_rows) return;
+    const unsigned int nb = (unsigned int)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
+    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, fstride, n_rows, nbr, area);
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets,
+                         const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, cudaStream_t s) {
+    if (!n_work) return;
+    const unsigned int nb = (unsigned int)((n_work * 32 + 127) / 128);
+    compact_redo_kernel<<<nb, 128, 0, s>>>(work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, fstride, n_work, nbr, area);
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s) {
+    if (!n_rows) return;
+    const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
+    compact_vertices_kernel<<<nb, 256, 0, s>>>(nverts, offsets, st_vtx, vstride, n_rows, vtx);
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s) {
+    constexpr int nb = 296;
+    double* partial = nullptr;
+    TESS_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(double) * nb, s));
+    volume_partial_kernel<<<nb, 256, 0, s>>>(vol, n, partial);
+    volume_final_kernel<<<1, 32, 0, s>>>(partial, nb, out);
+    TESS_CUDA_CHECK(cudaGetLastError());
+    TESS_CUDA_CHECK(cudaFreeAsync(partial, s));
+}
+
+}  // namespace tess

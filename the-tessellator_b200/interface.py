@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's public API (src/interface.rs) over the C ABI.
+
+Names, argument meaning and results follow interface.rs: `Diagram` (:25), `Cell` (:237),
+`VoronoiFace` (:393).  The reference computes one cell per call; here the first
+`Cell.compute_voronoi_cell()` for a given (search_radius, target_group) runs the whole diagram on
+the GPU once (tess_compute_all) and every cell reads its row of that batch.  `compute_all_cells`
+is the explicit batch entry point.
+
+Deviations (all forced by defects of the reference):
+  * add_particle_with_group / initialize are public (private in the reference, D3);
+  * the start polyhedron of a cell must be the diagram's container box (`Polyhedron(x_min, ...)`,
+    polyhedron.rs:226): the GPU path clips the axis-aligned container only;
+  * faces of the container that survive are reported with neighbour ids -1..-6 (D10).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+@dataclass(frozen=True)
+class Polyhedron:
+    """Start shape of a cell: the axis-aligned box of Polyhedron::new (polyhedron.rs:226-233)."""
+
+    x_min: float
+    y_min: float
+    z_min: float
+    x_max: float
+    y_max: float
+    z_max: float
+
+    def as_box(self) -> np.ndarray:
+        return np.array([self.x_min, self.y_min, self.z_min, self.x_max, self.y_max, self.z_max], dtype=np.float64)
+
+
+class CellBatch:
+    """All cells of one tess_compute_all call (CSR over cells)."""
+
+    def __init__(self, handle: int, device: int):
+        self._h = C.c_void_p(handle)
+        self.device = device
+        nc, nf = C.c_uint64(0), C.c_uint64(0)
+        check(_lib.lib().tess_result_n_cells(self._h, C.byref(nc), C.byref(nf)))
+        self.n_cells, self.n_faces = int(nc.value), int(nf.value)
+        self._cache = {}
+
+    def close(self):
+        if self._h:
+            _lib.lib().tess_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _view(self, fn: str, n: int, dtype) -> np.ndarray:
+        if fn not in self._cache:
+            p = C.c_void_p(0)
+            check(getattr(_lib.lib(), fn)(self._h, C.byref(p)))
+            if n == 0:
+                self._cache[fn] = np.zeros(0, dtype)
+            else:
+                buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(p.value)
+                self._cache[fn] = np.frombuffer(buf, dtype=dtype, count=n)  # view into the result's host buffer
+        return self._cache[fn]
+
+    @property
+    def volumes(self) -> np.ndarray:
+        return self._view("tess_result_volumes", self.n_cells, np.float64)
+
+    @property
+    def face_offsets(self) -> np.ndarray:
+        return self._view("tess_result_face_offsets", self.n_cells + 1, np.uint64).astype(np.int64)
+
+    @property
+    def neighbors(self) -> np.ndarray:
+        return self._view("tess_result_neighbors", self.n_faces, np.int64)
+
+    @property
+    def areas(self) -> np.ndarray:
+        return self._view("tess_result_areas", self.n_faces, np.float64)
+
+    @property
+    def status(self) -> np.ndarray:
+        return self._view("tess_result_status", self.n_cells, np.uint32)
+
+    @property
+    def cell_ids(self) -> np.ndarray:
+        return self._view("tess_result_cell_ids", self.n_cells, np.int64)
+
+    @property
+    def vertex_offsets(self) -> np.ndarray:
+        return self._view("tess_result_vertex_offsets", self.n_cells + 1, np.uint64).astype(np.int64)
+
+    @property
+    def vertices(self) -> np.ndarray:
+        nv = int(self.vertex_offsets[-1])
+        return self._view("tess_result_vertices", 3 * nv, np.float64).reshape(nv, 3)
+
+    def counters(self) -> dict:
+        arr = (C.c_uint64 * 8)()
+        check(_lib.lib().tess_result_counters(self._h, C.byref(arr)))
+        return {k: int(v) for k, v in zip(_lib.COUNTER_NAMES, arr)}
+
+    def volume_sum(self) -> float:
+        out = C.c_double(0)
+        check(_lib.lib().tess_result_volume_sum(self._h, C.byref(out)))
+        return float(out.value)
+
+    def device_views(self) -> dict:
+        ptrs = [C.c_void_p(0) for _ in range(6)]
+        check(_lib.lib().tess_result_device_views(self._h, *[C.byref(p) for p in ptrs]))
+        return dict(zip(("volumes", "face_offsets", "neighbors", "areas", "status", "cell_ids"), [p.value for p in ptrs]))
+
+    # per-cell slices
+    def cell_neighbors(self, row: int) -> np.ndarray:
+        o = self.face_offsets
+        return self.neighbors[o[row]:o[row + 1]]
+
+    def cell_areas(self, row: int) -> np.ndarray:
+        o = self.face_offsets
+        return self.areas[o[row]:o[row + 1]]
+
+    def cell_vertices(self, row: int) -> np.ndarray:
+        o = self.vertex_offsets
+        return self.vertices[o[row]:o[row + 1]]
+
+
+class Diagram:
+    """interface.rs:25 `Diagram`: particles + groups + spatial grid + container."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p(0)
+        check(_lib.lib().tess_diagram_create(C.byref(self._h), _lib.TESS_F64, device))
+        self.device = device
+        self.initialized = False
+        self._pending: list = []
+        self._pending_groups: list = []
+        self._n = 0
+        self._box: Optional[np.ndarray] = None
+        self._batches: dict = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for b in self._batches.values():
+                b.close()
+            self._batches = {}
+            _lib.lib().tess_diagram_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self._n + len(self._pending)
+
+    # ---- building (interface.rs:52-84) -------------------------------------------------------
+    def add_particle_with_group(self, particle: Sequence[float], group: int = 0) -> None:
+        """interface.rs:52-57.  `particle` exposes x, y, z (ToCeleryPoint, celery.rs:56-60)."""
+        if self.initialized:
+            raise _lib.TessError(-2, "particles must be added before initialize")
+        self._pending.append((float(particle[0]), float(particle[1]), float(particle[2])))
+        self._pending_groups.append(int(group))
+
+    def add_particles(self, xyz: np.ndarray, groups: Optional[np.ndarray] = None, stream: int = 0) -> None:
+        """Batch form of add_particle_with_group: xyz is (n, >=3) float64; row stride may exceed 24 B."""
+        self._flush()
+        a = np.asarray(xyz, dtype=np.float64)
+        if a.ndim != 2 or a.shape[1] < 3:
+            raise ValueError("xyz must be (n, >=3)")
+        if a.strides[1] != 8:
+            a = np.ascontiguousarray(a)
+        g = None if groups is None else np.ascontiguousarray(groups, dtype=np.uint64)
+        check(_lib.lib().tess_diagram_add_particles(self._h, a.ctypes.data, a.shape[0], a.strides[0], None if g is None else g.ctypes.data, stream))
+        self._n += a.shape[0]
+
+    def add_particles_device(self, xyz_ptr: int, n: int, groups_ptr: int = 0, ids_ptr: int = 0, stream: int = 0) -> None:
+        """Particles already resident in device memory (packed f64 triples)."""
+        self._flush()
+        check(_lib.lib().tess_diagram_add_particles_device(self._h, xyz_ptr, n, groups_ptr or None, ids_ptr or None, stream))
+        self._n += n
+
+    def _flush(self):
+        if self._pending:
+            pts = np.array(self._pending, dtype=np.float64)
+            grp = np.array(self._pending_groups, dtype=np.uint64)
+            self._pending, self._pending_groups = [], []
+            check(_lib.lib().tess_diagram_add_particles(self._h, pts.ctypes.data, pts.shape[0], 24, grp.ctypes.data, 0))
+            self._n += pts.shape[0]
+
+    def clear(self) -> None:
+        for b in self._batches.values():
+            b.close()
+        self._batches = {}
+        check(_lib.lib().tess_diagram_clear(self._h))
+        self._pending, self._pending_groups, self._n = [], [], 0
+        self.initialized = False
+
+    def initialize(self, container: Optional[Polyhedron] = None, stream: int = 0) -> None:
+        """interface.rs:60-84.  container None -> bounding box of the particles (:69-79)."""
+        self._flush()
+        box = None if container is None else container.as_box()
+        check(_lib.lib().tess_diagram_initialize(self._h, None if box is None else box.ctypes.data, stream))
+        self.initialized = True
+        if box is None:
+            b = self.grid_info()["bounds"]
+            box = np.array([b[0], b[2], b[4], b[1], b[3], b[5]])
+        self._box = box
+
+    def initialize_slab(self, container: Polyhedron, bounds, n_global: int, own, local, stream: int = 0) -> None:
+        self._flush()
+        box = container.as_box()
+        s = _lib.Slab()
+        for i in range(6):
+            s.bounds[i] = float(bounds[i])
+        s.n_global = int(n_global)
+        s.own_lo, s.own_hi = int(own[0]), int(own[1])
+        s.local_lo, s.local_hi = int(local[0]), int(local[1])
+        check(_lib.lib().tess_diagram_initialize_slab(self._h, box.ctypes.data, C.byref(s), stream))
+        self.initialized = True
+        self._box = box
+
+    # ---- grid facts (celery.rs) ---------------------------------------------------------------
+    def grid_info(self) -> dict:
+        n, cpd = C.c_uint64(0), C.c_uint64(0)
+        b, s, i = np.zeros(6), np.zeros(3), np.zeros(3)
+        check(_lib.lib().tess_diagram_grid_info(self._h, C.byref(n), C.byref(cpd), b.ctypes.data, s.ctypes.data, i.ctypes.data))
+        return dict(n_points=int(n.value), cells_per_dimension=int(cpd.value), bounds=b, cell_sizes=s, inverse_cell_sizes=i)
+
+    def copy_grid(self, n_local_cells: Optional[int] = None):
+        info = self.grid_info()
+        n = info["n_points"]
+        ncl = info["cells_per_dimension"] ** 3 if n_local_cells is None else n_local_cells
+        cells, sidx, delim = np.zeros(n, np.uint64), np.zeros(n, np.uint64), np.zeros(ncl + 1, np.uint64)
+        check(_lib.lib().tess_diagram_copy_grid(self._h, cells.ctypes.data, sidx.ctypes.data, delim.ctypes.data))
+        return cells, sidx, delim
+
+    def search_order(self, table_radius: int = 0):
+        ln, full = C.c_uint64(0), C.c_int(0)
+        check(_lib.lib().tess_diagram_copy_search_order(self._h, table_radius, C.byref(ln), None, None, C.byref(full)))
+        keys, ijk = np.zeros(ln.value), np.zeros(3 * ln.value, np.int32)
+        check(_lib.lib().tess_diagram_copy_search_order(self._h, table_radius, C.byref(ln), keys.ctypes.data, ijk.ctypes.data, C.byref(full)))
+        return keys, ijk.reshape(-1, 3), bool(full.value)
+
+    # ---- cells --------------------------------------------------------------------------------
+    def _opts(self, search_radius, target_group, outputs, table_radius, stream) -> _lib.Opts:
+        o = _lib.Opts()
+        _lib.lib().tess_opts_default(C.byref(o))
+        o.search_radius = float("nan") if search_radius is None else float(search_radius)
+        o.target_group = -1 if target_group is None else int(target_group)
+        if outputs is not None:
+            o.outputs = outputs
+        o.table_radius = table_radius
+        o.stream = stream or None
+        return o
+
+    def compute_all_cells(self, search_radius: Optional[float] = None, target_group: Optional[int] = None, outputs: Optional[int] = None,
+                          table_radius: int = 0, stream: int = 0) -> CellBatch:
+        """Batch fast path: every cell of the diagram in one call (tess_compute_all)."""
+        o = self._opts(search_radius, target_group, outputs, table_radius, stream)
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_compute_all(self._h, C.byref(o), C.byref(h)))
+        return CellBatch(h.value, self.device)
+
+    def compute_cells_at(self, points: np.ndarray, search_radius: Optional[float] = None, target_group: Optional[int] = None,
+                         outputs: Optional[int] = None, table_radius: int = 0, stream: int = 0) -> CellBatch:
+        """Batch form of get_cell_at_particle (interface.rs:211-232)."""
+        p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        o = self._opts(search_radius, target_group, outputs, table_radius, stream)
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_compute_at_points(self._h, p.ctypes.data, p.shape[0], C.byref(o), C.byref(h)))
+        return CellBatch(h.value, self.device)
+
+    def _check_polyhedron(self, polyhedron: Polyhedron):
+        if not np.array_equal(polyhedron.as_box(), self._box):
+            raise _lib.TessError(-5, "the start polyhedron of a cell must be the diagram's container box")
+
+    def _batch(self, search_radius, target_group) -> CellBatch:
+        key = (None if search_radius is None else float(search_radius), target_group)
+        if key not in self._batches:
+            self._batches[key] = self.compute_all_cells(search_radius, target_group, outputs=_lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | _lib.OUT_VERTICES)
+        return self._batches[key]
+
+    def get_cell_at_index(self, index: int, polyhedron: Polyhedron, search_radius: Optional[float] = None, target_group: Optional[int] = None) -> "Cell":
+        """interface.rs:186-208."""
+        self._check_polyhedron(polyhedron)
+        if not (0 <= index < self._n):
+            raise IndexError(index)
+        return Cell(self, index, None, search_radius, target_group)
+
+    def get_cell_at_particle(self, point: Sequence[float], polyhedron: Polyhedron, search_radius: Optional[float] = None, target_group: Optional[int] = None) -> "Cell":
+        """interface.rs:211-232."""
+        self._check_polyhedron(polyhedron)
+        return Cell(self, None, (float(point[0]), float(point[1]), float(point[2])), search_radius, target_group)
+
+
+class Cell:
+    """interface.rs:237 `Cell`."""
+
+    def __init__(self, diagram: Diagram, index: Optional[int], position, search_radius, target_group):
+        self.diagram, self.index, self.position = diagram, index, position
+        self.search_radius, self.target_group = search_radius, target_group
+        self._batch: Optional[CellBatch] = None
+        self._row = 0
+
+    def compute_voronoi_cell(self) -> None:
+        """interface.rs:257-313."""
+        if self.index is not None:
+            self._batch, self._row = self.diagram._batch(self.search_radius, self.target_group), self.index
+        else:
+            self._batch = self.diagram.compute_cells_at(
+                np.array([self.position]), self.search_radius, self.target_group,
+                outputs=_lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | _lib.OUT_VERTICES)
+            self._row = 0
+
+    def _need(self) -> CellBatch:
+        if self._batch is None:
+            self.compute_voronoi_cell()
+        return self._batch
+
+    def compute_volume(self) -> float:
+        """interface.rs:337-339."""
+        return float(self._need().volumes[self._row])
+
+    def compute_neighbors(self) -> list:
+        """interface.rs:342-344 (face order; container walls are -1..-6)."""
+        return [int(v) for v in self._need().cell_neighbors(self._row)]
+
+    def compute_vertices(self) -> np.ndarray:
+        """interface.rs:368-370: vertices in cell-local coordinates (relative to the particle)."""
+        return self._need().cell_vertices(self._row).copy()
+
+    def compute_faces(self) -> list:
+        """interface.rs:373-384."""
+        b = self._need()
+        lo, hi = int(b.face_offsets[self._row]), int(b.face_offsets[self._row + 1])
+        return [VoronoiFace(self, k) for k in range(lo, hi)]
+
+    def original_index(self) -> Optional[int]:
+        """interface.rs:387-389."""
+        return self.index
+
+    def status(self) -> int:
+        return int(self._need().status[self._row])
+
+
+class VoronoiFace:
+    """interface.rs:393 `VoronoiFace`."""
+
+    def __init__(self, cell: Cell, k: int):
+        self.cell, self._k = cell, k
+
+    def compute_area(self) -> float:
+        """interface.rs:408-410."""
+        return float(self.cell._batch.areas[self._k])
+
+    def compute_neighbor(self) -> int:
+        """interface.rs:413-416."""
+        return int(self.cell._batch.neighbors[self._k])
+
+
+def device_count() -> int:
+    return int(_lib.lib().tess_device_count())
+
+
+def isnan(x) -> bool:
+    return isinstance(x, float) and math.isnan(x)
