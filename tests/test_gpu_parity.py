@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bars (north_star / BASELINE.md §4):
+  * grid arrays, neighbour topology, status words and work counters: bit-exact;
+  * per-cell volumes and face areas: within 1e-12 relative (helpers.VOL_RTOL / AREA_RTOL);
+  * |sum of volumes - container volume| <= 1e-12 (relative to the container volume).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BOX = [0, 0, 0, 1, 1, 1]
+CNAMES = ("visited", "tested", "vertex_classifications", "cuts", "new_vertices", "table_entries", "degenerate_skips", "faces")
+ALL_OUT = 1 | 2 | 4 | 16
+
+
+def _diagram(tess, pts, box=BOX, groups=None):
+    d = tess.Diagram(0)
+    d.add_particles(pts, groups)
+    d.initialize(None if box is None else tess.Polyhedron(*box))
+    return d
+
+
+def test_device_and_library(tess):
+    assert tess.device_count() >= 1
+    assert os.path.exists(tess._lib.LIB_PATH)
+
+
+# ------------------------------------------------------------------ binning (K1-K4) ---------
+@pytest.mark.parametrize("case", ["n1", "n2", "n10", "n1000", "n100k", "oblong", "clustered", "bcc", "flat"])
+def test_grid_matches_oracle(tess, gen, ob, case):
+    pts = {
+        "n1": lambda: gen.uniform(1, 11),
+        "n2": lambda: gen.uniform(2, 11),
+        "n10": lambda: gen.uniform(10, 12),
+        "n1000": lambda: gen.uniform(1000, 13),
+        "n100k": lambda: gen.uniform(100_000, 14),
+        "oblong": lambda: gen.uniform(5000, 15) * np.array([1.0, 988.0, 10001.0]) + np.array([-5.0, 12.0, -10000.0]),
+        "clustered": lambda: gen.clustered(50_000, 4, k=8),
+        "bcc": lambda: gen.bcc(12, 5),
+        "flat": lambda: gen.uniform(3000, 16) * np.array([1.0, 1.0, 0.0]) + np.array([0.0, 0.0, 0.5]),  # zero z-extent
+    }[case]()
+    d = _diagram(tess, pts, box=None if case in ("oblong", "flat") else BOX)
+    od = ob.Diagram(pts, box=None if case in ("oblong", "flat") else BOX, table_radius=8)
+    gi = d.grid_info()
+    assert gi["cells_per_dimension"] == od.cpd
+    assert np.array_equal(gi["bounds"], od.bounds())
+    assert np.array_equal(np.concatenate([gi["cell_sizes"], gi["inverse_cell_sizes"]]), od.cell_info(), equal_nan=True)
+    cells, sidx, delim = d.copy_grid()
+    assert np.array_equal(cells, od.cells())
+    assert np.array_equal(sidx, od.sorted_indices())  # canonical in-cell order: ascending index
+    assert np.array_equal(delim, od.delimiters())
+    keys, ijk, full = d.search_order(8)
+    okeys, oijk = od.search_order()
+    assert full == od.table_is_full
+    assert np.array_equal(keys, okeys) and np.array_equal(ijk, oijk)
+    d.close()
+
+
+# ------------------------------------------------------------------ cells vs golden ---------
+FIXTURES = ["config1_uniform_10k_seed1.npz", "oblong_1500_seed9_bbox.npz", "clustered_4000_seed4.npz", "bcc_m8_seed5.npz", "simple_cubic_6.npz"]
+
+
+def _fixture_points(name, gen, g):
+    if name.startswith("config1"):
+        return gen.uniform(10_000, 1), BOX
+    if name.startswith("oblong"):
+        return gen.uniform(1500, 9) * np.array([1.0, 2.0, 0.5]) + np.array([-3.0, 10.0, 0.25]), None
+    if name.startswith("clustered"):
+        return g["points"], BOX
+    if name.startswith("bcc"):
+        return gen.bcc(8, 5), BOX
+    return gen.simple_cubic(6), BOX
+
+
+class _Gold:
+    def __init__(self, g):
+        self.volumes, self.face_offsets, self.neighbors, self.areas = g["volumes"], g["face_offsets"], g["neighbors"].astype(np.int64), g["areas"]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_cells_match_golden_fixture(tess, gen, name):
+    g = np.load(os.path.join(GOLD, name))
+    pts, box = _fixture_points(name, gen, g)
+    d = _diagram(tess, pts, box)
+    b = d.compute_all_cells(outputs=ALL_OUT)
+    helpers.assert_cells_match(b, _Gold(g), what=name)
+    c = b.counters()
+    assert [c[k] for k in CNAMES] == g["counters"].tolist()
+    if "status" in g.files:
+        assert np.array_equal(b.status, g["status"])  # degenerate skips flagged on the same cells
+    else:
+        assert np.all(b.status == 0)
+    d.close()
+
+
+# ------------------------------------------------------------------ cells vs live oracle ----
+@pytest.mark.parametrize("case", ["uniform200k", "clustered100k", "bcc16k", "tiny"])
+def test_cells_match_oracle(tess, gen, ob, case):
+    pts = {
+        "uniform200k": lambda: gen.uniform(200_000, 51),
+        "clustered100k": lambda: gen.clustered(100_000, 4, k=8),
+        "bcc16k": lambda: gen.bcc(20, 5),
+        "tiny": lambda: gen.uniform(5, 52),
+    }[case]()
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=ALL_OUT)
+    r = ob.Diagram(pts, box=BOX, table_radius=8).compute_cells(mode=ob.MODE_SECURITY)
+    ok = r.status == 0  # cells the oracle's own truncated table could finish
+    assert ok.mean() > 0.99
+    helpers_ok = _Subset(r, ok), _Subset(b, ok)
+    helpers.assert_cells_match(helpers_ok[1], helpers_ok[0], what=case)
+    assert np.all(b.status == 0)  # the GPU re-runs table-exhausted cells with a larger table
+    assert abs(b.volumes.sum() - 1.0) <= 1e-12
+    assert abs(b.volume_sum() - 1.0) <= 1e-12
+    if ok.all():
+        c = b.counters()
+        for k in ("tested", "vertex_classifications", "cuts", "new_vertices", "faces", "visited", "table_entries"):
+            if case == "clustered100k" and k in ("visited", "table_entries", "tested", "vertex_classifications", "cuts", "new_vertices"):
+                continue  # redone cells are counted by the first pass only
+            assert c[k] == r.counters[k], k
+    d.close()
+
+
+class _Subset:
+    """View of the cells selected by a boolean mask, in CSR form."""
+
+    def __init__(self, r, mask):
+        fo = np.asarray(r.face_offsets, np.int64)
+        cnt = np.diff(fo)[mask]
+        self.volumes = np.asarray(r.volumes)[mask]
+        self.face_offsets = np.concatenate([[0], np.cumsum(cnt)])
+        sel = np.repeat(mask, np.diff(fo))
+        self.neighbors = np.asarray(r.neighbors)[sel]
+        self.areas = np.asarray(r.areas)[sel]
+
+
+def test_exhausted_table_is_redone_not_wrong(tess, gen, ob):
+    """A deliberately tiny shell table (R=1) cannot terminate any cell; the redo pass with larger
+    tables must still deliver the exact cells."""
+    pts = gen.uniform(20_000, 53)
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=ALL_OUT, table_radius=1)
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
+    helpers.assert_cells_match(b, r, what="R=1")
+    assert np.all(b.status == 0)
+    d.close()
+
+
+def test_large_cell_path(tess, gen, ob):
+    """A particle surrounded by a dense shell has hundreds of faces: more than the small tables
+    hold (64 vertices / 40 faces), so it must come from the large-cell configuration."""
+    u = gen.uniform(600, 54)
+    th, ph = np.arccos(2 * u[:, 0] - 1), 2 * np.pi * u[:, 1]
+    shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
+    pts = np.concatenate([[[0.5, 0.5, 0.5]], shell, gen.uniform(2000, 55)[np.linalg.norm(gen.uniform(2000, 55) - 0.5, axis=1) > 0.35]])
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=ALL_OUT)
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
+    assert len(r.cell_neighbors(0)) > 100
+    helpers.assert_cells_match(b, r, what="shell")
+    assert np.all(b.status == 0)
+    assert abs(b.volumes.sum() - 1.0) <= 1e-12
+    d.close()
+
+
+def test_results_are_deterministic(tess, gen):
+    pts = gen.uniform(50_000, 56)
+    d = _diagram(tess, pts)
+    a = d.compute_all_cells()
+    b = d.compute_all_cells()
+    assert np.array_equal(a.volumes, b.volumes) and np.array_equal(a.neighbors, b.neighbors) and np.array_equal(a.areas, b.areas)
+    d2 = _diagram(tess, pts)
+    c = d2.compute_all_cells()
+    assert np.array_equal(a.volumes, c.volumes) and np.array_equal(a.neighbors, c.neighbors) and np.array_equal(a.areas, c.areas)
+    d.close()
+    d2.close()
+
+
+# ------------------------------------------------------------------ options ------------------
+def test_reference_radius_mode(tess, gen, ob):
+    pts = gen.uniform(20_000, 57)
+    d = _diagram(tess, pts)
+    od = ob.Diagram(pts, box=BOX)
+    sx = od.cell_info()[0]
+    for radius in (0.0, (1.5 * sx) ** 2, (4 * sx) ** 2):
+        b = d.compute_all_cells(search_radius=radius, outputs=ALL_OUT)
+        r = od.compute_cells(mode=ob.MODE_REFERENCE_RADIUS, search_radius=radius)
+        helpers.assert_cells_match(b, r, what=f"radius {radius}")
+        assert b.counters()["tested"] == r.counters["tested"]
+    d.close()
+
+
+def test_target_group(tess, gen, ob):
+    pts = gen.uniform(20_000, 58)
+    groups = (np.arange(len(pts)) % 3).astype(np.uint64)
+    d = _diagram(tess, pts, groups=groups)
+    od = ob.Diagram(pts, box=BOX, groups=groups)
+    for tg in (0, 2):
+        b = d.compute_all_cells(target_group=tg, outputs=ALL_OUT)
+        r = od.compute_cells(mode=ob.MODE_SECURITY, target_group=tg)
+        helpers.assert_cells_match(b, r, what=f"group {tg}")
+    # a group nobody carries: nothing cuts, every cell is the whole container
+    b = d.compute_all_cells(target_group=7)
+    assert np.all(b.volumes == 1.0) and np.all(np.diff(b.face_offsets) == 6)
+    d.close()
+
+
+def test_cells_at_query_points(tess, gen, ob):
+    pts = gen.uniform(20_000, 59)
+    d = _diagram(tess, pts)
+    od = ob.Diagram(pts, box=BOX)
+    q = gen.uniform(64, 60)
+    b = d.compute_cells_at(q, outputs=ALL_OUT)
+    for i in range(len(q)):
+        r = od.compute_cell_at_point(*q[i])
+        assert sorted(b.cell_neighbors(i).tolist()) == sorted(r.neighbors.tolist())
+        assert abs(b.volumes[i] - r.volumes[0]) <= 1e-12 * r.volumes[0]
+    d.close()
+
+
+def test_strided_host_input_and_incremental_adds(tess, gen, ob):
+    pts = gen.uniform(3000, 61)
+    rec = np.zeros((3000, 5))
+    rec[:, :3] = pts  # 40-byte records: x, y, z + two payload fields (ToCeleryPoint getters)
+    d = tess.Diagram(0)
+    d.add_particles(rec[:1000])
+    for p in pts[1000:1010]:
+        d.add_particle_with_group(p, 0)
+    d.add_particles(rec[1010:])
+    d.initialize(tess.Polyhedron(*BOX))
+    b = d.compute_all_cells()
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
+    helpers.assert_cells_match(b, r, what="strided")
+    d.close()
+
+
+# ------------------------------------------------------------------ reference-shaped API -----
+def test_per_cell_api_reads_like_the_reference(tess, gen, ob):
+    """interface.rs usage: diagram.get_cell_at_index(i, Polyhedron::new(box), None, None) ->
+    compute_voronoi_cell -> compute_volume / compute_neighbors / compute_faces."""
+    pts = gen.uniform(2000, 62)
+    diagram = tess.Diagram()
+    for p in pts:
+        diagram.add_particle_with_group(p, 0)
+    diagram.initialize(tess.Polyhedron(*BOX))
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY, want_vertices=True)
+    for i in (0, 7, 1999):
+        cell = diagram.get_cell_at_index(i, tess.Polyhedron(*BOX), None, None)
+        cell.compute_voronoi_cell()
+        assert abs(cell.compute_volume() - r.volumes[i]) <= 1e-12 * r.volumes[i]
+        assert sorted(cell.compute_neighbors()) == sorted(r.cell_neighbors(i).tolist())
+        faces = cell.compute_faces()
+        assert len(faces) == len(r.cell_neighbors(i))
+        got = sorted((f.compute_neighbor(), f.compute_area()) for f in faces)
+        exp = sorted(zip(r.cell_neighbors(i).tolist(), r.cell_areas(i).tolist()))
+        for (gn, ga), (en, ea) in zip(got, exp):
+            assert gn == en and abs(ga - ea) <= 1e-12 * ea
+        assert cell.original_index() == i
+        # vertices: same set of cell-local coordinates (bitwise), order unspecified
+        gv = {tuple(v) for v in cell.compute_vertices()}
+        ev = {tuple(v) for v in r.cell_vertices(i)}
+        assert gv == ev
+    with pytest.raises(tess.TessError):
+        diagram.get_cell_at_index(0, tess.Polyhedron(0, 0, 0, 2, 2, 2))
+    with pytest.raises(tess.TessError):
+        diagram.add_particle_with_group((0.5, 0.5, 0.5), 0)  # after initialize (interface.rs:50-51)
+    diagram.close()
+
+
+def test_error_behaviour(tess):
+    d = tess.Diagram(0)
+    with pytest.raises(tess.TessError) as e:
+        d.initialize(tess.Polyhedron(*BOX))  # empty: CeleryBounds::new panics (celery.rs:82)
+    assert e.value.code == -1
+    with pytest.raises(tess.TessError) as e:
+        d.compute_all_cells()
+    assert e.value.code == -2
+    d.close()
+
+
+# ------------------------------------------------------------------ slab mode on one device --
+def test_slab_decomposition_is_bit_identical(tess, gen):
+    """Fake multi-GPU: G slabs computed one after the other on one device with host-side halo
+    selection; every cell must equal the whole-domain run bit for bit (same kernel, same grid
+    parameters, same candidate order)."""
+    pts = gen.uniform(60_000, 63)
+    whole = _diagram(tess, pts)
+    wb = whole.compute_all_cells()
+    gi = whole.grid_info()
+    cpd, b = gi["cells_per_dimension"], gi["bounds"]
+    gx = np.minimum(((pts[:, 0] - b[0]) * gi["inverse_cell_sizes"][0]).astype(np.int64), cpd - 1)
+    gx[pts[:, 0] >= b[1]] = cpd - 1
+    G, h = 3, 4
+    cuts = [0, cpd // 3, 2 * cpd // 3, cpd]
+    seen = np.zeros(len(pts), bool)
+    for g in range(G):
+        own = (cuts[g], cuts[g + 1])
+        local = (max(0, own[0] - h), min(cpd, own[1] + h))
+        sel = np.nonzero((gx >= local[0]) & (gx < local[1]))[0]
+        # shuffle the local arrival order: the canonical in-cell order must not depend on it
+        sel = sel[np.argsort(gen.u01(7, sel.astype(np.uint64)))]
+        d = tess.Diagram(0)
+        import torch
+
+        xyz = torch.from_numpy(pts[sel]).cuda()
+        ids = torch.from_numpy(sel.astype(np.int64)).cuda()
+        d.add_particles_device(xyz.data_ptr(), len(sel), ids_ptr=ids.data_ptr())
+        d.initialize_slab(tess.Polyhedron(*BOX), b, len(pts), own, local)
+        sb = d.compute_all_cells()
+        assert np.all((sb.status & 8) == 0)  # halo of 4 planes is enough for uniform input
+        ids_out = sb.cell_ids
+        assert np.all((gx[ids_out] >= own[0]) & (gx[ids_out] < own[1]))
+        seen[ids_out] = True
+        assert np.array_equal(sb.volumes, wb.volumes[ids_out])
+        wfo = wb.face_offsets
+        for k in range(0, len(ids_out), 997):
+            i = ids_out[k]
+            assert np.array_equal(sb.cell_neighbors(k), wb.neighbors[wfo[i]:wfo[i + 1]])
+            assert np.array_equal(sb.cell_areas(k), wb.areas[wfo[i]:wfo[i + 1]])
+        d.close()
+    assert seen.all()
+    # a halo that is too thin is reported per cell, never silently wrong
+    own, local = (cuts[1], cuts[2]), (cuts[1] - 1, cuts[2] + 1)
+    sel = np.nonzero((gx >= local[0]) & (gx < local[1]))[0]
+    d = tess.Diagram(0)
+    import torch
+
+    xyz = torch.from_numpy(pts[sel]).cuda()
+    ids = torch.from_numpy(sel.astype(np.int64)).cuda()
+    d.add_particles_device(xyz.data_ptr(), len(sel), ids_ptr=ids.data_ptr())
+    d.initialize_slab(tess.Polyhedron(*BOX), b, len(pts), own, local)
+    sb = d.compute_all_cells()
+    flagged = (sb.status & 8) != 0
+    assert flagged.any()
+    okc = ~flagged
+    assert np.array_equal(sb.volumes[okc], wb.volumes[sb.cell_ids[okc]])
+    d.close()
+    whole.close()
+
+
+# ------------------------------------------------------------------ full-size configs --------
+def _full_size_checks(tess, gen, ob, pts, sample_seed, n_sample):
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=ALL_OUT)
+    n = len(pts)
+    assert np.all(b.status == 0)
+    assert abs(b.volume_sum() - 1.0) <= 1e-12
+    assert abs(float(np.sum(b.volumes)) - 1.0) <= 1e-12
+    assert np.all(b.volumes > 0) and np.all(b.areas >= 0)
+    assert helpers.neighbor_symmetry_violations(b.face_offsets, b.neighbors) == 0
+    # oracle on a sample of cells
+    ids = np.unique((gen.u01(sample_seed, np.arange(n_sample, dtype=np.uint64)) * n).astype(np.uint64))
+    r = ob.Diagram(pts, box=BOX, table_radius=8).compute_cells(ids=ids, mode=ob.MODE_SECURITY)
+    mask = np.zeros(n, bool)
+    mask[ids.astype(np.int64)] = True
+    helpers.assert_cells_match(_Subset(b, mask), r, what=f"sample of {len(ids)}")
+    d.close()
+
+
+def test_config2_one_million_uniform(tess, gen, ob):
+    _full_size_checks(tess, gen, ob, gen.uniform(1_000_000, 2), 71, 20_000)
+
+
+def test_config3_ten_million_uniform(tess, gen, ob):
+    _full_size_checks(tess, gen, ob, gen.uniform(10_000_000, 3), 72, 5_000)

@@ -1,0 +1,239 @@
+"""Slab-sharded Voronoi cell construction: one process per GPU, torch.distributed for the plumbing.
+
+The path shards by spatial slab: cells depend only on particles within their
+termination radius, and grid cell ids are x-major (celery.rs:323-324), so a slab of grid x-planes
+plus a halo of `h` planes on each side is everything a rank needs.
+
+    bounds      all-reduce(min/max) of 6 scalars          -> identical grid parameters everywhere
+    histogram   all-reduce(sum) of particles per x-plane  -> equal-count slab cuts
+    exchange    all-to-all(v) of (xyz, id) records        -> every rank receives its owned planes
+                                                             plus the halo planes (ghost particles)
+    compute     tess_diagram_initialize_slab + tess_compute_all on the local planes
+    verify      any cell whose search reached a plane outside the halo is flagged
+                (TESS_STATUS_HALO_INSUFFICIENT); the exchange is redone with a wider halo.
+
+Every rank bins with the same global bounds / cpd and orders candidates inside a grid cell by
+global particle id, so per-cell results are bit-identical to the single-GPU run.
+
+The compute backend is injected (`SlabBackend`): the product backend drives the CUDA library on
+torch CUDA tensors; the CPU tests inject a numpy backend to exercise this host logic under gloo.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def cells_per_dimension(n_global: int) -> int:
+    """celery.rs:161-162 with libm cbrt (math.cbrt is glibc's); saturating cast."""
+    v = math.cbrt(n_global / 1.25)
+    return (int(v) if v > 0 else 0) + 1
+
+
+def slab_cuts(plane_counts: np.ndarray, n_ranks: int) -> List[int]:
+    """Plane indices c[0]=0 <= ... <= c[n_ranks]=cpd such that every slab [c[g], c[g+1]) holds
+    about the same number of particles (prefix sum of the per-plane histogram)."""
+    cpd = len(plane_counts)
+    total = int(plane_counts.sum())
+    pre = np.concatenate([[0], np.cumsum(plane_counts.astype(np.int64))])
+    cuts = [0]
+    for g in range(1, n_ranks):
+        target = total * g / n_ranks
+        c = int(np.searchsorted(pre, target, side="left"))
+        # choose the nearer of the two neighbouring plane boundaries
+        if c > 0 and abs(pre[c - 1] - target) <= abs(pre[min(c, cpd)] - target):
+            c -= 1
+        c = max(cuts[-1], min(c, cpd))
+        cuts.append(c)
+    cuts.append(cpd)
+    # every rank must own at least one plane when there are enough planes
+    if cpd >= n_ranks:
+        for g in range(1, n_ranks):
+            cuts[g] = max(cuts[g], cuts[g - 1] + 1)
+        for g in range(n_ranks - 1, 0, -1):
+            cuts[g] = min(cuts[g], cuts[g + 1] - 1)
+    return cuts
+
+
+def receive_ranges(cuts: Sequence[int], halo: int) -> Tuple[List[int], List[int]]:
+    cpd = cuts[-1]
+    lo = [max(0, cuts[g] - halo) for g in range(len(cuts) - 1)]
+    hi = [min(cpd, cuts[g + 1] + halo) for g in range(len(cuts) - 1)]
+    return lo, hi
+
+
+@dataclass
+class SlabResult:
+    """Per-rank outcome: rows are the owned cells in the rank's grid order."""
+
+    batch: object            # CellBatch (or whatever the backend returns)
+    own: Tuple[int, int]
+    local: Tuple[int, int]
+    n_owned: int
+    halo: int
+    n_received: int
+    rounds: int
+
+
+class SlabBackend:
+    """What the host logic needs from a compute backend.  Arrays are torch tensors on the
+    backend's device."""
+
+    device = None
+
+    def bounds(self, xyz):  # -> tensor[6] f64: x_min,x_max,y_min,y_max,z_min,z_max
+        raise NotImplementedError
+
+    def plane_histogram(self, xyz, bounds6: np.ndarray, n_global: int):  # -> tensor[cpd] int64
+        raise NotImplementedError
+
+    def pack(self, xyz, id_base: int, bounds6, n_global, lo, hi):  # -> (counts list[int], xyz_packed, ids_packed)
+        raise NotImplementedError
+
+    def compute(self, xyz, ids, box, bounds6, n_global, own, local, opts):  # -> (batch, n_owned, any_halo_flag: bool)
+        raise NotImplementedError
+
+
+class CudaSlabBackend(SlabBackend):
+    """Product backend: libtess_b200 on torch CUDA tensors of the current device."""
+
+    def __init__(self, device_index: int):
+        import torch
+
+        from . import _lib
+        from .interface import Diagram
+
+        self._torch, self._lib, self._Diagram = torch, _lib, Diagram
+        self.device_index = device_index
+        self.device = torch.device("cuda", device_index)
+        self._diagram = None
+
+    def _stream(self) -> int:
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def bounds(self, xyz):
+        out = self._torch.empty(6, dtype=self._torch.float64, device=self.device)
+        self._lib.check(self._lib.lib().tess_bounds(xyz.data_ptr(), xyz.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def plane_histogram(self, xyz, bounds6, n_global):
+        cpd = cells_per_dimension(n_global)
+        out = self._torch.empty(cpd, dtype=self._torch.int64, device=self.device)
+        b = np.ascontiguousarray(bounds6, dtype=np.float64)
+        self._lib.check(self._lib.lib().tess_plane_histogram(xyz.data_ptr(), xyz.shape[0], b.ctypes.data, n_global, out.data_ptr(), self._stream()))
+        return out
+
+    def pack(self, xyz, id_base, bounds6, n_global, lo, hi):
+        torch = self._torch
+        n, R = xyz.shape[0], len(lo)
+        b = np.ascontiguousarray(bounds6, dtype=np.float64)
+        plo, phi = np.ascontiguousarray(lo, dtype=np.uint32), np.ascontiguousarray(hi, dtype=np.uint32)
+        counts = torch.empty(R, dtype=torch.int64, device=self.device)
+        cap = int(n * 1.5) + 1024
+        while True:
+            oxyz = torch.empty((cap, 3), dtype=torch.float64, device=self.device)
+            oids = torch.empty(cap, dtype=torch.int64, device=self.device)
+            rc = self._lib.lib().tess_pack_for_slabs(xyz.data_ptr(), None, id_base, n, b.ctypes.data, n_global, R, plo.ctypes.data, phi.ctypes.data,
+                                                     counts.data_ptr(), oxyz.data_ptr(), oids.data_ptr(), cap, self._stream())
+            c = [int(v) for v in counts.cpu().tolist()]
+            if rc == 0:
+                tot = sum(c)
+                return c, oxyz[:tot], oids[:tot]
+            if rc != -4:
+                self._lib.check(rc)
+            cap = sum(c) + 1024
+
+    def compute(self, xyz, ids, box, bounds6, n_global, own, local, opts):
+        from .interface import Polyhedron
+
+        if self._diagram is None:
+            self._diagram = self._Diagram(self.device_index)
+        d = self._diagram
+        d.clear()
+        s = self._stream()
+        d.add_particles_device(xyz.data_ptr(), xyz.shape[0], ids_ptr=ids.data_ptr(), stream=s)
+        d.initialize_slab(Polyhedron(*box), bounds6, n_global, own, local, stream=s)
+        batch = d.compute_all_cells(stream=s, **opts)
+        flagged = False
+        if batch.n_cells:
+            # status words stay on the device: one tiny reduction tells whether any halo was too thin
+            st = _as_tensor(self._torch, batch.device_views()["status"], batch.n_cells, self._torch.int32, self.device)
+            flagged = bool(((st & self._lib.STATUS_HALO_INSUFFICIENT) != 0).any().item())
+        return batch, batch.n_cells, flagged
+
+
+def _as_tensor(torch, ptr: int, n: int, dtype, device):
+    """Zero-copy torch view of library-owned device memory (valid while the result lives)."""
+    class _Holder:
+        pass
+
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    h = _Holder()
+    h.__cuda_array_interface__ = {
+        "shape": (n,), "typestr": {4: "<i4", 8: "<i8"}[itemsize] if dtype in (torch.int32, torch.int64) else "<f8",
+        "data": (ptr, False), "version": 2, "strides": None,
+    }
+    return torch.as_tensor(h, device=device)
+
+
+def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int, box: Sequence[float], dist=None, halo: int = 4,
+                    max_rounds: int = 4, opts: Optional[dict] = None, bounds6: Optional[np.ndarray] = None) -> SlabResult:
+    """Run the sharded hot path on this rank.
+
+    xyz_local : (n_local, 3) f64 tensor on the backend's device — an arbitrary subset of the global
+                particle set (global ids id_base .. id_base+n_local-1).
+    dist      : torch.distributed (initialised) or None for a single process.
+    """
+    import torch
+
+    opts = dict(opts or {})
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+
+    # ---- global bounds: CeleryBounds::new (celery.rs:81-125) over ALL particles ---------------
+    if bounds6 is None:
+        b = backend.bounds(xyz_local)
+        if dist is not None and world > 1:
+            mins, maxs = b[0::2].clone(), b[1::2].clone()
+            dist.all_reduce(mins, op=dist.ReduceOp.MIN)
+            dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+            b = torch.stack([mins, maxs], dim=1).reshape(-1)
+        bounds6 = b.cpu().numpy().astype(np.float64)
+    cpd = cells_per_dimension(n_global)
+
+    # ---- equal-count slab cuts from the per-plane histogram ----------------------------------
+    hist = backend.plane_histogram(xyz_local, bounds6, n_global)
+    if dist is not None and world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    cuts = slab_cuts(hist.cpu().numpy(), world)
+
+    rounds = 0
+    while True:
+        rounds += 1
+        lo, hi = receive_ranges(cuts, halo)
+        # ---- ghost-particle exchange: all-to-all(v) of (xyz, id) -----------------------------
+        send_counts, sxyz, sids = backend.pack(xyz_local, id_base, bounds6, n_global, lo, hi)
+        if dist is not None and world > 1:
+            sc = torch.tensor(send_counts, dtype=torch.int64, device=sxyz.device)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc)
+            recv_counts = [int(v) for v in rc.cpu().tolist()]
+            rxyz = torch.empty((sum(recv_counts), 3), dtype=sxyz.dtype, device=sxyz.device)
+            rids = torch.empty(sum(recv_counts), dtype=sids.dtype, device=sids.device)
+            dist.all_to_all_single(rxyz, sxyz, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+            dist.all_to_all_single(rids, sids, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+        else:
+            rxyz, rids = sxyz, sids
+        own = (cuts[rank], cuts[rank + 1])
+        local = (lo[rank], hi[rank])
+        batch, n_owned, flagged = backend.compute(rxyz, rids, box, bounds6, n_global, own, local, opts)
+        # ---- was any halo too thin? ----------------------------------------------------------
+        flag = torch.tensor([1 if flagged else 0], dtype=torch.int32, device=rxyz.device)
+        if dist is not None and world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0 or rounds >= max_rounds or halo >= cpd:
+            return SlabResult(batch=batch, own=own, local=local, n_owned=n_owned, halo=halo, n_received=int(rxyz.shape[0]), rounds=rounds)
+        halo = min(cpd, 2 * halo)
