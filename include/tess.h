@@ -157,6 +157,10 @@ int tess_result_vertices(tess_result* r, const double** out);         /* xyz tri
 int tess_result_counters(tess_result* r, uint64_t counters[8]);
 /* Sum of all volumes computed on the device (closure check: equals the container volume). */
 int tess_result_volume_sum(tess_result* r, double* out);
+/* Copy results into caller-owned host buffers (pinned memory makes the copies asynchronous and
+ * full-speed).  Any pointer may be NULL; sizes are those of the host views above.  The copies are
+ * enqueued on `stream`; the caller synchronises. */
+int tess_result_download(const tess_result* r, double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas, uint32_t* status, void* stream);
 /* Device views for callers that keep results on the GPU (any pointer may be NULL). */
 int tess_result_device_views(const tess_result* r, const double** volumes, const uint64_t** face_offsets, const int64_t** neighbors, const double** areas, const uint32_t** status, const int64_t** cell_ids);
 
@@ -172,6 +176,19 @@ int tess_bounds(const double* xyz_dev, size_t n, double* bounds_dev, void* strea
  * after rank, out_xyz_dev / out_ids_dev (capacity `cap` particles).  ids_dev = ids of the inputs
  * (NULL -> id_base + i).  Returns TESS_ERR_NOMEM if cap is too small (send_counts_dev still valid). */
 int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t id_base, size_t n, const double bounds[6], uint64_t n_global, int n_ranks, const uint32_t* plane_lo, const uint32_t* plane_hi, uint64_t* send_counts_dev, double* out_xyz_dev, int64_t* out_ids_dev, size_t cap, void* stream);
+
+/* ---- Telemetry used by bench.py ----------------------------------------------------------- */
+
+/* CUDA-event durations (ms, on the launching stream) of the last computation:
+ * ms[0] clip kernel (small-cell pass), ms[1] large-cell redo pass, ms[2] scans + CSR compaction, ms[3] whole call. */
+int tess_result_timings(const tess_result* r, double ms[4]);
+/* ms[0] = binning pass (histogram + scan + scatter + gather) of the last initialize. */
+int tess_diagram_timings(const tess_diagram* d, double ms[1]);
+/* Number of CUDA kernels this library has launched in this process so far. */
+uint64_t tess_kernel_launch_count(void);
+/* Measures the device's FP64 FMA throughput with a register-resident DFMA loop (a denominator for
+ * the clip kernel's roofline; MEASURED_PEAKS.json has no FP64 figure).  Result in TFLOP/s. */
+int tess_measure_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

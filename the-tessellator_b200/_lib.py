@@ -30,6 +30,7 @@ SYMBOLS = (
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
     "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs",
+    "tess_result_download", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
 
 
@@ -120,6 +121,11 @@ def lib() -> C.CDLL:
     sig("tess_result_counters", ci, vp, P(u64 * 8))
     sig("tess_result_volume_sum", ci, vp, P(f64))
     sig("tess_result_device_views", ci, vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(vp))
+    sig("tess_result_download", ci, vp, vp, vp, vp, vp, vp, vp)
+    sig("tess_kernel_launch_count", u64)
+    sig("tess_result_timings", ci, vp, P(f64 * 4))
+    sig("tess_diagram_timings", ci, vp, P(f64 * 1))
+    sig("tess_measure_fp64_peak", ci, ci, P(f64))
     sig("tess_plane_histogram", ci, vp, sz, vp, u64, vp, vp)
     sig("tess_bounds", ci, vp, sz, vp, vp)
     sig("tess_pack_for_slabs", ci, vp, vp, i64, sz, vp, u64, ci, vp, vp, vp, vp, vp, sz, vp)

@@ -9,7 +9,10 @@
 //     |i|,|j|,|k| <= R and to keys strictly below min_axis sq(R*size) so that it is an exact
 //     prefix of the reference's full (2cpd-1)^3 table, ordered canonically by (key, i, j, k).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -136,6 +139,22 @@ void build_shell_table(const GridSpec& g, int R, std::vector<ShellEntry>& out, b
 
 constexpr int kDefaultTableRadius = 8;
 
+// TESS_TRACE=1: host-side phase timings on stderr (wall clock, each phase closed by a stream sync)
+struct Trace {
+    bool on;
+    cudaStream_t s;
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    Trace(const char* w, cudaStream_t st) : on(std::getenv("TESS_TRACE") != nullptr), s(st), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* phase) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[tess trace] %s / %-24s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 }  // namespace
 
 struct tess_diagram {
@@ -152,8 +171,11 @@ struct tess_diagram {
     size_t n_cells_local = 0;
     DevBuf counts, delim, cell_of, rank_in_cell, tmp_idx, sorted, sorted_idx, slot_of, groups_sorted, scan_tmp, small;
     uint32_t own_slot_begin = 0, own_slot_end = 0;
+    cudaEvent_t ev_bin0 = nullptr, ev_bin1 = nullptr;  // around K2-K4 of the last initialize
     mutable std::mutex mu;
     mutable std::map<int, ShellTable> tables;
+    uint32_t table_cpd = 0;
+    double table_size[3] = {0, 0, 0};
 
     const ShellTable& table(int R, cudaStream_t s) const {
         std::lock_guard<std::mutex> lk(mu);
@@ -173,8 +195,9 @@ struct tess_diagram {
 
 struct tess_result {
     int device = 0;
+    cudaStream_t stream = nullptr;  // stream the arrays were allocated on (stream-ordered allocator)
     uint64_t n_cells = 0, n_faces = 0, n_vertices = 0;
-    // device arrays (cudaMalloc)
+    // device arrays (cudaMallocAsync on `stream`: cached by the device's memory pool between steps)
     double* vol = nullptr;
     uint32_t* nfaces = nullptr;
     uint32_t* status = nullptr;
@@ -186,6 +209,8 @@ struct tess_result {
     uint64_t* voffsets = nullptr;
     double* vtx = nullptr;
     unsigned long long* counters = nullptr;
+    unsigned long long counters_redo[CNT_N] = {0, 0, 0, 0, 0, 0, 0, 0};  // work done by the large-cell pass
+    double ms_clip = 0, ms_redo = 0, ms_outputs = 0, ms_total = 0;  // CUDA-event durations on the launching stream
     // host copies
     std::vector<double> h_vol, h_area, h_vtx;
     std::vector<uint64_t> h_offsets, h_voffsets;
@@ -195,7 +220,7 @@ struct tess_result {
     ~tess_result() {
         cudaSetDevice(device);
         for (void* p : {(void*)vol, (void*)nfaces, (void*)status, (void*)cell_id, (void*)offsets, (void*)nbr, (void*)area, (void*)nverts, (void*)voffsets, (void*)vtx, (void*)counters})
-            if (p) cudaFree(p);
+            if (p) cudaFreeAsync(p, stream);
     }
 };
 
@@ -275,6 +300,8 @@ void tess_diagram_destroy(tess_diagram* d) {
                       &d->groups_sorted, &d->scan_tmp, &d->small})
         b->release();
     for (auto& kv : d->tables) kv.second.dev.release();
+    if (d->ev_bin0) cudaEventDestroy(d->ev_bin0);
+    if (d->ev_bin1) cudaEventDestroy(d->ev_bin1);
     delete d;
 }
 
@@ -341,16 +368,14 @@ int tess_diagram_clear(tess_diagram* d) {
     d->has_groups = d->has_ids = false;
     d->initialized = false;
     d->slab = false;
-    std::lock_guard<std::mutex> lk(d->mu);
-    for (auto& kv : d->tables) kv.second.dev.release();
-    d->tables.clear();
-    return TESS_OK;
+    return TESS_OK;  // shell tables are kept: initialize drops them only if the grid geometry changes
 }
 
 static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* slab, cudaStream_t s) {
     if (d->initialized) return fail(TESS_ERR_STATE, "diagram already initialized (interface.rs:65)");
     if (d->n == 0) return fail(TESS_ERR_INVALID, "no particles (CeleryBounds::new panics on an empty set, celery.rs:82)");
     TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    Trace tr("initialize", s);
     const size_t n = d->n;
     d->small.reserve(256);
     double* dev_bounds = d->small.as<double>();             // 6 doubles
@@ -393,7 +418,13 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
     d->slot_of.reserve(sizeof(uint32_t) * n);
     if (d->has_groups) d->groups_sorted.reserve(sizeof(uint64_t) * n);
     d->scan_tmp.reserve(scan_tmp_bytes(ncl + 1));
+    tr.mark("bounds+reserve");
 
+    if (!d->ev_bin0) {
+        TESS_CUDA_CHECK(cudaEventCreate(&d->ev_bin0));
+        TESS_CUDA_CHECK(cudaEventCreate(&d->ev_bin1));
+    }
+    TESS_CUDA_CHECK(cudaEventRecord(d->ev_bin0, s));
     TESS_CUDA_CHECK(cudaMemsetAsync(d->counts.p, 0, sizeof(uint32_t) * (ncl + 1), s));
     TESS_CUDA_CHECK(cudaMemsetAsync(dev_flag, 0, sizeof(uint32_t), s));
     // K2: cell ids + histogram
@@ -411,6 +442,8 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
     launch_rank_fix_gather(d->tmp_idx.as<uint32_t>(), d->cell_of.as<uint32_t>(), d->delim.as<uint32_t>(), d->xyz.as<double>(), d->has_ids ? d->ids.as<int64_t>() : nullptr,
                            d->has_groups ? d->groups.as<uint64_t>() : nullptr, d->sorted.as<Particle>(), d->sorted_idx.as<uint32_t>(), d->slot_of.as<uint32_t>(),
                            d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr, n, s);
+    TESS_CUDA_CHECK(cudaEventRecord(d->ev_bin1, s));
+    tr.mark("binning kernels");
     if (slab) {
         uint32_t b = 0, e = 0;
         const size_t cb = static_cast<size_t>(g.own_lo - g.local_lo) * g.cpd * g.cpd, ce = static_cast<size_t>(g.own_hi - g.local_lo) * g.cpd * g.cpd;
@@ -424,9 +457,15 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
         d->own_slot_end = static_cast<uint32_t>(n);
     }
     {
+        // the search-order tables depend only on cpd and the cell sizes (celery.rs:423-427)
         std::lock_guard<std::mutex> lk(d->mu);
-        for (auto& kv : d->tables) kv.second.dev.release();
-        d->tables.clear();
+        const bool same = d->table_cpd == g.cpd && d->table_size[0] == g.sx && d->table_size[1] == g.sy && d->table_size[2] == g.sz;
+        if (!same) {
+            for (auto& kv : d->tables) kv.second.dev.release();
+            d->tables.clear();
+            d->table_cpd = g.cpd;
+            d->table_size[0] = g.sx; d->table_size[1] = g.sy; d->table_size[2] = g.sz;
+        }
     }
     d->initialized = true;
     return TESS_OK;
@@ -506,9 +545,9 @@ int tess_diagram_copy_search_order(const tess_diagram* d, int32_t table_radius, 
 namespace {
 
 template <class T>
-T* dmalloc(size_t count) {
+T* dmalloc(size_t count, cudaStream_t s) {
     void* p = nullptr;
-    TESS_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T)));
+    TESS_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(1, count) * sizeof(T), s));
     return static_cast<T*>(p);
 }
 
@@ -543,20 +582,22 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     const bool want_vtx = (o.outputs & TESS_OUT_VERTICES) != 0;
     const bool want_cnt = (o.outputs & TESS_OUT_COUNTERS) != 0;
 
+    Trace tr("compute", s);
     std::unique_ptr<tess_result> r(new tess_result());
     r->device = d->device;
+    r->stream = s;
     r->n_cells = n_rows;
-    r->vol = dmalloc<double>(n_rows);
-    r->nfaces = dmalloc<uint32_t>(n_rows + 1);
-    r->status = dmalloc<uint32_t>(n_rows);
-    r->cell_id = dmalloc<int64_t>(n_rows);
-    r->offsets = dmalloc<uint64_t>(n_rows + 1);
-    r->counters = dmalloc<unsigned long long>(CNT_N);
+    r->vol = dmalloc<double>(n_rows, s);
+    r->nfaces = dmalloc<uint32_t>(n_rows + 1, s);
+    r->status = dmalloc<uint32_t>(n_rows, s);
+    r->cell_id = dmalloc<int64_t>(n_rows, s);
+    r->offsets = dmalloc<uint64_t>(n_rows + 1, s);
+    r->counters = dmalloc<unsigned long long>(CNT_N, s);
     TESS_CUDA_CHECK(cudaMemsetAsync(r->counters, 0, sizeof(unsigned long long) * CNT_N, s));
     TESS_CUDA_CHECK(cudaMemsetAsync(r->nfaces, 0, sizeof(uint32_t) * (n_rows + 1), s));
     if (want_vtx) {
-        r->nverts = dmalloc<uint32_t>(n_rows + 1);
-        r->voffsets = dmalloc<uint64_t>(n_rows + 1);
+        r->nverts = dmalloc<uint32_t>(n_rows + 1, s);
+        r->voffsets = dmalloc<uint64_t>(n_rows + 1, s);
         TESS_CUDA_CHECK(cudaMemsetAsync(r->nverts, 0, sizeof(uint32_t) * (n_rows + 1), s));
     }
     if (n_rows == 0) {
@@ -582,8 +623,10 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     }
     void* scan_tmp = tmp.get<char>(scan_tmp_bytes(n_rows + 1));
     TESS_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 8, s));
+    tr.mark("allocations");
 
     const ShellTable& tab = d->table(R0, s);
+    tr.mark("shell table");
     ClipParams P{};
     P.sorted = d->sorted.as<Particle>();
     P.delim = d->delim.as<uint32_t>();
@@ -611,7 +654,15 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.n_failed = ctrl + 1;
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
+    cudaEvent_t ev[5];
+    for (auto& e : ev) TESS_CUDA_CHECK(cudaEventCreate(&e));
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); }
+    } ev_guard{ev};
+    TESS_CUDA_CHECK(cudaEventRecord(ev[0], s));
     launch_clip(P, /*large=*/false, s);
+    TESS_CUDA_CHECK(cudaEventRecord(ev[1], s));
 
     // CSR offsets; one sync fetches {n_failed, total}
     launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
@@ -620,6 +671,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     TESS_CUDA_CHECK(cudaMemcpyAsync(&n_failed, ctrl + 1, sizeof(n_failed), cudaMemcpyDeviceToHost, s));
     TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    tr.mark("clip + scan");
 
     // ---- redo pass: cells the small tables / the default shell table could not finish ----------
     uint32_t n_redo = 0;
@@ -632,6 +684,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         lg_nbr = tmp.get<int64_t>((size_t)n_redo * lstride);
         lg_area = want_area ? tmp.get<double>((size_t)n_redo * lstride) : nullptr;
         uint32_t* failed2 = tmp.get<uint32_t>(n_redo);
+        unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
         int R = R0;
         const int cpd_m1 = static_cast<int>(d->grid.cpd) - 1;
         for (int attempt = 0; attempt < 12; ++attempt) {
@@ -645,7 +698,8 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.work_slots = failed;
             Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.fstride = lstride; Q.stage_by_work = 1;
             Q.st_vtx = nullptr;  // vertices of large cells are not staged (TESS_OUT_VERTICES covers small cells only)
-            Q.counters = nullptr;
+            Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
+            if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
             Q.failed_slots = failed2;
             Q.n_failed = ctrl + 2;
             Q.failed_cap = n_redo;
@@ -657,14 +711,22 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             TESS_CUDA_CHECK(cudaStreamSynchronize(s));
             if (still == 0 || t2.full) break;  // remaining failures (if any) are capacity overflows: reported in status
         }
+        if (want_cnt) {
+            unsigned long long h[CNT_N];
+            TESS_CUDA_CHECK(cudaMemcpyAsync(h, redo_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+            TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+            for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] = h[i];
+        }
         launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
         TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaStreamSynchronize(s));
     }
 
+    tr.mark("redo");
+    TESS_CUDA_CHECK(cudaEventRecord(ev[2], s));
     r->n_faces = total;
-    r->nbr = dmalloc<int64_t>(total);
-    if (want_area) r->area = dmalloc<double>(total);
+    r->nbr = dmalloc<int64_t>(total, s);
+    if (want_area) r->area = dmalloc<double>(total, s);
     launch_compact_faces(r->status, r->offsets, st_nbr, st_area, fstride, n_rows, r->nbr, r->area, s);
     if (n_redo)
         launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lstride, n_redo, r->nbr, r->area, s);
@@ -674,10 +736,23 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         TESS_CUDA_CHECK(cudaMemcpyAsync(&tv, r->voffsets + n_rows, sizeof(tv), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaStreamSynchronize(s));
         r->n_vertices = tv;
-        r->vtx = dmalloc<double>(3 * tv);
+        r->vtx = dmalloc<double>(3 * tv, s);
         launch_compact_vertices(r->nverts, r->voffsets, st_vtx, vstride, n_rows, r->vtx, s);
     }
+    TESS_CUDA_CHECK(cudaEventRecord(ev[3], s));
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    tr.mark("alloc out + compaction");
+    {
+        float a = 0, b = 0, c = 0, t = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        cudaEventElapsedTime(&t, ev[0], ev[3]);
+        r->ms_clip = a;
+        r->ms_redo = n_redo ? b : 0.0;  // includes the (small) scans before/after the redo pass
+        r->ms_outputs = c + (n_redo ? 0.0 : b);
+        r->ms_total = t;
+    }
     *out = r.release();
     return TESS_OK;
 }
@@ -765,7 +840,7 @@ int tess_result_counters(tess_result* r, uint64_t counters[8]) {
     cudaSetDevice(r->device);
     unsigned long long h[CNT_N];
     TESS_CUDA_CHECK(cudaMemcpy(h, r->counters, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; ++i) counters[i] = h[i];
+    for (int i = 0; i < 8; ++i) counters[i] = h[i] + r->counters_redo[i];
     return TESS_OK;
     TESS_CATCH
 }
@@ -774,10 +849,55 @@ int tess_result_volume_sum(tess_result* r, double* out) {
     if (!r || !out) return fail(TESS_ERR_INVALID, "NULL argument");
     TESS_TRY
     cudaSetDevice(r->device);
-    double* dsum = dmalloc<double>(1);
-    launch_volume_sum(r->vol, r->n_cells, dsum, nullptr);
-    TESS_CUDA_CHECK(cudaMemcpy(out, dsum, sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dsum);
+    cudaStream_t s = r->stream;
+    double* dsum = dmalloc<double>(1, s);
+    launch_volume_sum(r->vol, r->n_cells, dsum, s);
+    TESS_CUDA_CHECK(cudaMemcpyAsync(out, dsum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFreeAsync(dsum, s);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_result_download(const tess_result* r, double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas, uint32_t* status, void* stream) {
+    if (!r) return fail(TESS_ERR_INVALID, "NULL result");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TESS_CUDA_CHECK(cudaSetDevice(r->device));
+    if (volumes && r->n_cells) TESS_CUDA_CHECK(cudaMemcpyAsync(volumes, r->vol, sizeof(double) * r->n_cells, cudaMemcpyDeviceToHost, s));
+    if (face_offsets) TESS_CUDA_CHECK(cudaMemcpyAsync(face_offsets, r->offsets, sizeof(uint64_t) * (r->n_cells + 1), cudaMemcpyDeviceToHost, s));
+    if (neighbors && r->n_faces) TESS_CUDA_CHECK(cudaMemcpyAsync(neighbors, r->nbr, sizeof(int64_t) * r->n_faces, cudaMemcpyDeviceToHost, s));
+    if (areas && r->n_faces) {
+        if (!r->area) return fail(TESS_ERR_STATE, "areas were not requested in tess_opts.outputs");
+        TESS_CUDA_CHECK(cudaMemcpyAsync(areas, r->area, sizeof(double) * r->n_faces, cudaMemcpyDeviceToHost, s));
+    }
+    if (status && r->n_cells) TESS_CUDA_CHECK(cudaMemcpyAsync(status, r->status, sizeof(uint32_t) * r->n_cells, cudaMemcpyDeviceToHost, s));
+    return TESS_OK;
+    TESS_CATCH
+}
+
+uint64_t tess_kernel_launch_count(void) { return launch_count(); }
+
+int tess_result_timings(const tess_result* r, double ms[4]) {
+    if (!r || !ms) return fail(TESS_ERR_INVALID, "NULL argument");
+    ms[0] = r->ms_clip; ms[1] = r->ms_redo; ms[2] = r->ms_outputs; ms[3] = r->ms_total;
+    return TESS_OK;
+}
+
+int tess_diagram_timings(const tess_diagram* d, double ms[1]) {
+    if (!d || !ms) return fail(TESS_ERR_INVALID, "NULL argument");
+    if (!d->initialized || !d->ev_bin0) return fail(TESS_ERR_STATE, "diagram not initialized");
+    float t = 0;
+    if (cudaEventSynchronize(d->ev_bin1) != cudaSuccess || cudaEventElapsedTime(&t, d->ev_bin0, d->ev_bin1) != cudaSuccess) return fail(TESS_ERR_CUDA, "event timing failed");
+    ms[0] = t;
+    return TESS_OK;
+}
+
+int tess_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    TESS_CUDA_CHECK(cudaSetDevice(device));
+    *tflops = measure_fp64_peak_tflops();
     return TESS_OK;
     TESS_CATCH
 }

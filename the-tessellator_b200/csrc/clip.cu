@@ -37,6 +37,11 @@ namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
 
+// Start cube: {flip, target, next} of the 24 half-edges (ids of polyhedron.rs:97-199)
+__constant__ uint32_t kCubeEdges[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x050200u, 0x110205u, 0x030106u, 0x170507u, 0x090604u,
+                                        0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
+                                        0x000211u, 0x040612u, 0x080713u, 0x0c0310u, 0x020015u, 0x0e0416u, 0x0a0517u, 0x060114u};
+
 // ---------------------------------------------------------------------------------------------
 // Bit masks over table slots.  Small cells keep them in registers, large cells in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -127,11 +132,11 @@ struct WarpSmem {
     long long fnbr[Cfg::FMAX];
     typename Cfg::EdgeWord edge[Cfg::EMAX];  // {next, flip, target, face}
     typename Cfg::Idx fstart[Cfg::FMAX];
+    typename Cfg::Idx estack[Cfg::EMAX];     // free half-edge slots (LIFO, like pool.rs's free list)
     // masks of the large configuration live here (1-word placeholders otherwise)
     uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
         m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
     uint32_t m_flive[Cfg::REG ? 1 : Cfg::FMAX / 32], m_fkeep[Cfg::REG ? 1 : Cfg::FMAX / 32];
-    uint32_t m_elive[Cfg::REG ? 1 : Cfg::EMAX / 32];
 };
 
 template <class Cfg, int NW>
@@ -148,15 +153,31 @@ struct Mesh {
     WarpSmem<Cfg>* sm;
     MaskT<Cfg, NWV> vlive, vbefore, inside, outside, removed;
     MaskT<Cfg, NWF> flive, fkeep;
-    MaskT<Cfg, NWE> elive;
+    // Half-edge slots: [0, e_hwm) have been handed out at least once; a free slot holds FREE_EDGE
+    // and sits on the LIFO stack sm->estack[0, e_top) — the shape of pool.rs's Pool (free list +
+    // append at the end) without a per-slot bitmask.
+    int e_top, e_hwm;
     int lane;
+    static constexpr EW FREE_EDGE = ~(EW)0;
+    static __device__ __forceinline__ bool e_is_free(EW w) { return e_face(w) == Cfg::NONE; }
+    __device__ __forceinline__ int alloc_edge() {
+        if (e_top > 0) return (int)sm->estack[--e_top];
+        if (e_hwm < Cfg::E_LIMIT) return e_hwm++;
+        return -1;
+    }
+    // edge word of slot 32*p+lane, FREE_EDGE beyond the high-water mark
+    __device__ __forceinline__ EW edge_of_pass(int p) const {
+        const int e = 32 * p + lane;
+        return e < e_hwm ? sm->edge[e] : FREE_EDGE;
+    }
+    __device__ __forceinline__ int edge_passes() const { return (e_hwm + 31) >> 5; }
 
     __device__ __forceinline__ void bind(WarpSmem<Cfg>* s, int lane_) {
         sm = s;
         lane = lane_;
         if constexpr (!Cfg::REG) {
             vlive.w = s->m_vlive; vbefore.w = s->m_vbefore; inside.w = s->m_inside; outside.w = s->m_outside; removed.w = s->m_removed;
-            flive.w = s->m_flive; fkeep.w = s->m_fkeep; elive.w = s->m_elive;
+            flive.w = s->m_flive; fkeep.w = s->m_fkeep;
         }
     }
 
@@ -172,7 +193,9 @@ struct Mesh {
 
     // Polyhedron::build_cube (polyhedron.rs:268-392) translated by -p (interface.rs:266).
     __device__ void build_cube(const double* box, double px, double py, double pz) {
-        vlive.clear(); flive.clear(); elive.clear();
+        vlive.clear(); flive.clear();
+        e_top = 0;
+        e_hwm = 24;
         __syncwarp();
         if (lane < 8) {
             // FDL FDR FUR FUL BDL BDR BUR BUL (polyhedron.rs:288-295); corner + (-p)
@@ -185,10 +208,7 @@ struct Mesh {
         }
         if (lane < 24) {
             // {flip, target, next} per half-edge, ids of polyhedron.rs:97-199 (DR belongs to face D)
-            const uint32_t T[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x050200u, 0x110205u, 0x030106u, 0x170507u, 0x090604u,
-                                    0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
-                                    0x000211u, 0x040612u, 0x080713u, 0x0c0310u, 0x020015u, 0x0e0416u, 0x0a0517u, 0x060114u};
-            const uint32_t t = T[lane];
+            const uint32_t t = kCubeEdges[lane];
             sm->edge[lane] = pack(t & 0xFFu, (t >> 16) & 0xFFu, (t >> 8) & 0xFFu, (uint32_t)lane >> 2);
         }
         if (lane < 6) {
@@ -197,7 +217,6 @@ struct Mesh {
         }
         vlive.set_word(0, 0xFFu);
         flive.set_word(0, 0x3Fu);
-        elive.set_word(0, 0xFFFFFFu);
         __syncwarp();
     }
 
@@ -227,7 +246,7 @@ struct Mesh {
 // Returns 0 = no cut, 1 = cut, 2 = skipped (D17), <0 = capacity overflow / inconsistency.
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, unsigned long long& cnt_vc, unsigned long long& cnt_nv) {
+__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
     WarpSmem<Cfg>* sm = M.sm;
@@ -263,19 +282,14 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     // ---- first edge (slot order) with target Inside whose flip's target is Outside; the walk
     //      starts on the flip (polyhedron.rs:413-432) ---------------------------------------------
     int first = -1;
-#pragma unroll
-    for (int p = 0; p < MeshT::NWE; ++p) {
-        if (first >= 0) break;
-        const uint32_t lw = M.elive.word(p);
-        if (lw == 0u) continue;
+    const int n_pass = M.edge_passes();
+    for (int p = 0; p < n_pass && first < 0; ++p) {
+        const EW w = M.edge_of_pass(p);
         bool hit = false;
         uint32_t fl = 0;
-        if ((lw >> lane) & 1u) {
-            const EW w = sm->edge[32 * p + lane];
-            if (M.inside.test(MeshT::e_tgt(w))) {
-                fl = MeshT::e_flip(w);
-                hit = M.outside.test(MeshT::e_tgt(sm->edge[fl]));
-            }
+        if (!MeshT::e_is_free(w) && M.inside.test(MeshT::e_tgt(w))) {
+            fl = MeshT::e_flip(w);
+            hit = M.outside.test(MeshT::e_tgt(sm->edge[fl]));
         }
         const uint32_t hm = __ballot_sync(FULL, hit);
         if (hm) first = (int)__shfl_sync(FULL, fl, __ffs(hm) - 1);
@@ -286,7 +300,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     }
 
     // ---- the walk (polyhedron.rs:475-623), warp-uniform ---------------------------------------
-    const int cap_first = M.elive.alloc(Cfg::E_LIMIT);
+    const int cap_first = M.alloc_edge();
     const int cap_face = M.flive.alloc(Cfg::FMAX);
     if (cap_first < 0 || cap_face < 0) return -1;
     sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (polyhedron.rs:479-482)
@@ -322,7 +336,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         M.set_field(out_e, 2, prev_int);  // :550
         if (need) {                       // :552-601
             const int nv = M.vlive.alloc(Cfg::VMAX);
-            const int br = M.elive.alloc(Cfg::E_LIMIT);
+            const int br = M.alloc_edge();
             if (nv < 0 || br < 0) return -1;
             Vec3 x;
             const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
@@ -345,7 +359,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             } else {
                 // the cap edge paired with this bridge: the reference creates it at the end of the
                 // previous crossing (:592-598) with target = previous intersection
-                const int ce = M.elive.alloc(Cfg::E_LIMIT);
+                const int ce = M.alloc_edge();
                 if (ce < 0) return -1;
                 capk = (uint32_t)ce;
                 sm->edge[capk] = MeshT::pack(cap_prev, (uint32_t)br, prev_int, (uint32_t)cap_face);
@@ -381,13 +395,11 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         int it = 0;
         while (changed && it++ < Cfg::VMAX) {
             changed = false;
-#pragma unroll 1
-            for (int p = 0; p < MeshT::NWE; ++p) {
-                const uint32_t lw = M.elive.word(p);
-                if (lw == 0u) continue;
+            const int np = M.edge_passes();
+            for (int p = 0; p < np; ++p) {
                 uint32_t add_v = Cfg::NONE;
-                if ((lw >> lane) & 1u) {
-                    const EW w = sm->edge[32 * p + lane];
+                const EW w = M.edge_of_pass(p);
+                if (!MeshT::e_is_free(w)) {
                     const uint32_t t = MeshT::e_tgt(w), fl = MeshT::e_flip(w);
                     if (t != Cfg::NONE && fl != Cfg::NONE) {
                         const uint32_t s = MeshT::e_tgt(sm->edge[fl]);
@@ -413,15 +425,14 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     M.fkeep.clear();
     if constexpr (!Cfg::REG) __syncwarp();
     bool inconsistent = false;
-#pragma unroll
-    for (int p = 0; p < MeshT::NWE; ++p) {
-        const uint32_t lw = M.elive.word(p);
-        if (lw == 0u) continue;
+    const int old_top = M.e_top;
+    const int n_pass2 = M.edge_passes();
+    for (int p = 0; p < n_pass2; ++p) {
         bool dead = false;
         uint32_t face = 0;
-        const bool live = (lw >> lane) & 1u;
+        const EW w = M.edge_of_pass(p);
+        const bool live = !MeshT::e_is_free(w);
         if (live) {
-            const EW w = sm->edge[32 * p + lane];
             const uint32_t t = MeshT::e_tgt(w);
             const uint32_t s = MeshT::e_tgt(sm->edge[MeshT::e_flip(w)]);
             const bool tr = M.removed.test(t), sr = M.removed.test(s);
@@ -429,8 +440,12 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             inconsistent |= (tr != sr);
             face = MeshT::e_face(w);
         }
+        // retire dead half-edges: mark the slot free and push it on the free stack (ascending slot order)
         const uint32_t dm = __ballot_sync(FULL, dead);
-        M.elive.set_word(p, lw & ~dm);
+        if (dead) {
+            sm->estack[M.e_top + __popc(dm & ((1u << lane) - 1u))] = (typename Cfg::Idx)(32 * p + lane);
+        }
+        M.e_top += __popc(dm);
         const bool keep = live && !dead;  // this half-edge keeps its face alive
         if constexpr (Cfg::REG) {
 #pragma unroll
@@ -443,6 +458,8 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         }
     }
     __syncwarp();
+    // only now overwrite the retired slots (their words were still needed as flips above)
+    for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
     if (__any_sync(FULL, inconsistent)) status |= ST_INCONSISTENT;
 #pragma unroll
     for (int q = 0; q < MeshT::NWF; ++q) M.flive.set_word(q, M.flive.word(q) & M.fkeep.word(q));
@@ -453,7 +470,8 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 // ---------------------------------------------------------------------------------------------
 // The kernel: persistent warps pull cells from a work counter.
 // ---------------------------------------------------------------------------------------------
-template <class Cfg>
+// COUNT: also accumulate the work counters (a separate instantiation keeps them out of the timed kernel).
+template <class Cfg, bool COUNT>
 __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams P) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
@@ -466,13 +484,14 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams 
     const GridSpec& G = P.grid;
     const int cpd = (int)G.cpd;
     const bool radius_mode = !(P.search_radius != P.search_radius);  // not NaN
-    unsigned long long c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0, c_deg = 0, c_faces = 0;
+    unsigned long long t_vis = 0, t_test = 0, t_vc = 0, t_cuts = 0, t_nv = 0, t_tab = 0, t_deg = 0, t_faces = 0;  // totals of finished cells
 
     for (;;) {
         uint32_t work = 0;
         if (lane == 0) work = atomicAdd(P.work_counter, 1u);
         work = __shfl_sync(FULL, work, 0);
         if (work >= P.n_work) break;
+        uint32_t c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0, c_deg = 0;  // this cell
 
         // ---- the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207) -----------
         double px, py, pz;
@@ -637,7 +656,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams 
         double vol_part = 0.0;
         uint32_t rank_base = 0;
         if (!failed) {
-#pragma unroll 1
+#pragma unroll
             for (int q = 0; q < MeshT::NWF; ++q) {
                 const uint32_t lw = M.flive.word(q);
                 if (lw == 0u) continue;
@@ -680,7 +699,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams 
         for (int o = 16; o > 0; o >>= 1) vol_part = addd(vol_part, __shfl_xor_sync(FULL, vol_part, o));
         if (P.st_vtx && !failed) {
             uint32_t vb = 0;
-#pragma unroll 1
+#pragma unroll
             for (int p = 0; p < MeshT::NWV; ++p) {
                 const uint32_t lw = M.vlive.word(p);
                 if ((lw >> lane) & 1u) {
@@ -709,49 +728,59 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams 
             P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
             if (P.cell_id) P.cell_id[row] = self_id;
         }
-        c_faces += nf;
+        if (COUNT && (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT | ST_TABLE_EXHAUSTED)) == 0) {
+            // only cells this pass finished are counted; the others are counted by the redo pass
+            t_vis += c_vis; t_test += c_test; t_vc += c_vc; t_cuts += c_cuts; t_nv += c_nv; t_tab += c_tab; t_deg += c_deg; t_faces += nf;
+        }
         __syncwarp();
     }
 
-    if (P.counters && lane == 0) {
-        atomicAdd(&P.counters[CNT_VISITED], c_vis);
-        atomicAdd(&P.counters[CNT_TESTED], c_test);
-        atomicAdd(&P.counters[CNT_VC], c_vc);
-        atomicAdd(&P.counters[CNT_CUTS], c_cuts);
-        atomicAdd(&P.counters[CNT_NV], c_nv);
-        atomicAdd(&P.counters[CNT_TABLE], c_tab);
-        atomicAdd(&P.counters[CNT_DEGEN], c_deg);
-        atomicAdd(&P.counters[CNT_FACES], c_faces);
+    if (COUNT && P.counters && lane == 0) {
+        atomicAdd(&P.counters[CNT_VISITED], t_vis);
+        atomicAdd(&P.counters[CNT_TESTED], t_test);
+        atomicAdd(&P.counters[CNT_VC], t_vc);
+        atomicAdd(&P.counters[CNT_CUTS], t_cuts);
+        atomicAdd(&P.counters[CNT_NV], t_nv);
+        atomicAdd(&P.counters[CNT_TABLE], t_tab);
+        atomicAdd(&P.counters[CNT_DEGEN], t_deg);
+        atomicAdd(&P.counters[CNT_FACES], t_faces);
     }
 }
 
-template <class Cfg>
+template <class Cfg, bool COUNT>
 void launch_cfg(const ClipParams& p, cudaStream_t s) {
     if (!p.n_work) return;
     const size_t smem = sizeof(WarpSmem<Cfg>) * Cfg::WARPS;
     static bool configured = false;
+    static int per_sm_cached = 0, sms_cached = 0;
     if (!configured) {
-        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        TESS_CUDA_CHECK(cudaGetDevice(&dev));
+        TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev));
+        TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, clip_kernel<Cfg, COUNT>, Cfg::WARPS * 32, smem));
         configured = true;
     }
-    int dev = 0, sms = 148, per_sm = 1;
-    TESS_CUDA_CHECK(cudaGetDevice(&dev));
-    TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, clip_kernel<Cfg>, Cfg::WARPS * 32, smem));
+    int sms = sms_cached, per_sm = per_sm_cached;
     if (per_sm < 1) per_sm = 1;
     // persistent grid: a whole number of resident waves (148 SMs x resident CTAs)
     const unsigned int want = (unsigned int)((p.n_work + Cfg::WARPS - 1) / Cfg::WARPS);
     const unsigned int grid = std::min<unsigned int>(want, (unsigned int)(sms * per_sm));
     TESS_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s));
-    clip_kernel<Cfg><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
+    clip_kernel<Cfg, COUNT><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
 
 void launch_clip(const ClipParams& p, bool large, cudaStream_t s) {
-    if (large) launch_cfg<LargeCfg>(p, s);
-    else launch_cfg<SmallCfg>(p, s);
+    const bool count = p.counters != nullptr;
+    if (large) {
+        if (count) launch_cfg<LargeCfg, true>(p, s); else launch_cfg<LargeCfg, false>(p, s);
+    } else {
+        if (count) launch_cfg<SmallCfg, true>(p, s); else launch_cfg<SmallCfg, false>(p, s);
+    }
 }
 uint32_t clip_small_fmax() { return SmallCfg::FMAX; }
 uint32_t clip_small_vmax() { return SmallCfg::VMAX; }

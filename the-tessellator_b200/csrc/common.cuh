@@ -92,6 +92,10 @@ struct ClipParams {
             throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__)); \
     } while (0)
 
+// every kernel launch of the library is counted (tess_kernel_launch_count)
+void note_launch(int n = 1);
+unsigned long long launch_count();
+
 // kernels' host launchers (grid.cu / clip.cu / outputs.cu)
 void launch_bounds(const double* xyz, size_t n, double* bounds6, cudaStream_t s);
 void launch_cell_histogram(const double* xyz, size_t n, const GridSpec& g, uint32_t* cell_of, uint32_t* rank_in_cell, uint32_t* counts, uint32_t* oob_flag, cudaStream_t s);
@@ -114,5 +118,6 @@ void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const
 void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, cudaStream_t s);
 void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s);
 void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s);
+double measure_fp64_peak_tflops();
 
 }  // namespace tess

@@ -341,7 +341,9 @@ void launch_bounds(const double* xyz, size_t n, double* bounds6, cudaStream_t s)
     const size_t npairs = (n + 1) / 2;
     const int nb = (int)std::min<size_t>(kBoundsBlocks, std::max<size_t>(1, (npairs + kThreads - 1) / kThreads));
     bounds_partial_kernel<<<nb, kThreads, 0, s>>>(xyz, n, partial, aligned16(xyz));
+    note_launch();
     bounds_final_kernel<<<1, 32, 0, s>>>(partial, nb, bounds6);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
     TESS_CUDA_CHECK(cudaFreeAsync(partial, s));
 }
@@ -350,6 +352,7 @@ void launch_cell_histogram(const double* xyz, size_t n, const GridSpec& g, uint3
     const size_t npairs = (n + 1) / 2;
     if (!npairs) return;
     cell_histogram_kernel<<<blocks_for(npairs, kThreads), kThreads, 0, s>>>(xyz, n, g, cell_of, rank_in_cell, counts, oob_flag, aligned16(xyz));
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -368,6 +371,7 @@ static void launch_scan_impl(const uint32_t* in, OutT* out, size_t n, void* tmp,
     unsigned long long* state = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tmp) + 16);
     const size_t tiles = (n + kScanTile - 1) / kScanTile;
     scan_kernel<OutT><<<(unsigned int)tiles, kThreads, 0, s>>>(in, out, n, counter, state);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 void launch_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* tmp, size_t tmp_bytes, cudaStream_t s) { launch_scan_impl<uint32_t>(in, out, n, tmp, tmp_bytes, s); }
@@ -378,6 +382,7 @@ void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t 
 void launch_scatter(const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, uint32_t* tmp_idx, size_t n, cudaStream_t s) {
     if (!n) return;
     scatter_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(cell_of, rank_in_cell, delim, tmp_idx, n);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -385,18 +390,21 @@ void launch_rank_fix_gather(const uint32_t* tmp_idx, const uint32_t* cell_of, co
                             Particle* sorted, uint32_t* sorted_idx, uint32_t* slot_of, uint64_t* groups_sorted, size_t n, cudaStream_t s) {
     if (!n) return;
     rank_fix_gather_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(tmp_idx, cell_of, delim, xyz, ids, groups, sorted, sorted_idx, slot_of, groups_sorted, n);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_plane_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s) {
     if (!n) return;
     plane_histogram_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, n, g, counts);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, unsigned long long* counts, cudaStream_t s) {
     if (!n) return;
     pack_count_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, n, g, n_ranks, lo_dev, hi_dev, counts);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -404,6 +412,7 @@ void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base,
                          const unsigned long long* offsets, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, cudaStream_t s) {
     if (!n) return;
     pack_scatter_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, ids, id_base, n, g, n_ranks, lo_dev, hi_dev, offsets, cursors, out_xyz, out_ids);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 

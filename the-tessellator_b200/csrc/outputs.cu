@@ -3,6 +3,8 @@
 // The clip kernel leaves each cell's neighbour ids / face areas in a fixed-stride staging row
 // (the batched form of the Vec returns of interface.rs:342-384).  After an exclusive scan of the
 // face counts these kernels pack the rows into CSR arrays with coalesced writes.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace tess {
@@ -95,6 +97,7 @@ void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
     compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, fstride, n_rows, nbr, area);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -103,6 +106,7 @@ void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot
     if (!n_work) return;
     const unsigned int nb = (unsigned int)((n_work * 32 + 127) / 128);
     compact_redo_kernel<<<nb, 128, 0, s>>>(work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, fstride, n_work, nbr, area);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -110,6 +114,7 @@ void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, co
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
     compact_vertices_kernel<<<nb, 256, 0, s>>>(nverts, offsets, st_vtx, vstride, n_rows, vtx);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -118,9 +123,61 @@ void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s)
     double* partial = nullptr;
     TESS_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(double) * nb, s));
     volume_partial_kernel<<<nb, 256, 0, s>>>(vol, n, partial);
+    note_launch();
     volume_final_kernel<<<1, 32, 0, s>>>(partial, nb, out);
+    note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
     TESS_CUDA_CHECK(cudaFreeAsync(partial, s));
 }
 
+}  // namespace tess
+
+// ---------------------------------------------------------------------------------------------
+// telemetry
+// ---------------------------------------------------------------------------------------------
+#include <atomic>
+namespace tess {
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+
+// 8 independent DFMA chains per thread, everything in registers.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace
+
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+double measure_fp64_peak_tflops() {
+    int dev = 0, sms = 148;
+    TESS_CUDA_CHECK(cudaGetDevice(&dev));
+    TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    double* out = nullptr;
+    TESS_CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    TESS_CUDA_CHECK(cudaEventCreate(&e0));
+    TESS_CUDA_CHECK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        TESS_CUDA_CHECK(cudaEventRecord(e0));
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        TESS_CUDA_CHECK(cudaEventRecord(e1));
+        TESS_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        TESS_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
 }  // namespace tess

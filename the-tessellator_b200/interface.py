@@ -116,6 +116,17 @@ class CellBatch:
         check(_lib.lib().tess_result_volume_sum(self._h, C.byref(out)))
         return float(out.value)
 
+    def timings(self) -> dict:
+        """CUDA-event durations in ms: clip kernel, large-cell redo, scans + compaction, whole call."""
+        arr = (C.c_double * 4)()
+        check(_lib.lib().tess_result_timings(self._h, C.byref(arr)))
+        return dict(clip_ms=arr[0], redo_ms=arr[1], outputs_ms=arr[2], total_ms=arr[3])
+
+    def download(self, volumes=None, face_offsets=None, neighbors=None, areas=None, status=None, stream: int = 0) -> None:
+        """Asynchronous copies into caller-owned (ideally pinned) host arrays; the caller synchronises."""
+        ptr = lambda a: None if a is None else a.ctypes.data if hasattr(a, "ctypes") else a.data_ptr()  # noqa: E731
+        check(_lib.lib().tess_result_download(self._h, ptr(volumes), ptr(face_offsets), ptr(neighbors), ptr(areas), ptr(status), stream or None))
+
     def device_views(self) -> dict:
         ptrs = [C.c_void_p(0) for _ in range(6)]
         check(_lib.lib().tess_result_device_views(self._h, *[C.byref(p) for p in ptrs]))
@@ -238,6 +249,11 @@ class Diagram:
         b, s, i = np.zeros(6), np.zeros(3), np.zeros(3)
         check(_lib.lib().tess_diagram_grid_info(self._h, C.byref(n), C.byref(cpd), b.ctypes.data, s.ctypes.data, i.ctypes.data))
         return dict(n_points=int(n.value), cells_per_dimension=int(cpd.value), bounds=b, cell_sizes=s, inverse_cell_sizes=i)
+
+    def binning_ms(self) -> float:
+        arr = (C.c_double * 1)()
+        check(_lib.lib().tess_diagram_timings(self._h, C.byref(arr)))
+        return float(arr[0])
 
     def copy_grid(self, n_local_cells: Optional[int] = None):
         info = self.grid_info()
