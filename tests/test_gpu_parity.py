@@ -186,6 +186,30 @@ def test_results_are_deterministic(tess, gen):
     d2.close()
 
 
+def test_parallel_cut_equals_serial_walk(tess, gen, tmp_path):
+    """The kernel cuts in lane-parallel form when no vertex lies on the plane and falls back to the
+    reference-shaped serial walk otherwise.  TESS_FORCE_SERIAL=1 disables the fast path: both must
+    give bit-identical volumes, areas and face order."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, importlib, numpy as np; sys.path.insert(0, %r);"
+        "T = importlib.import_module('the-tessellator_b200');"
+        "pts = np.concatenate([T.generators.uniform(150000, 5), T.generators.bcc(20, 5)]);"
+        "d = T.Diagram(0); d.add_particles(pts); d.initialize(T.Polyhedron(0, 0, 0, 1, 1, 1));"
+        "b = d.compute_all_cells(outputs=7);"
+        "np.savez(sys.argv[1], v=b.volumes, n=b.neighbors, a=b.areas, o=b.face_offsets, s=b.status)"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("par", {}), ("ser", {"TESS_FORCE_SERIAL": "1"})):
+        f = str(tmp_path / f"{tag}.npz")
+        subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, **env))
+        outs[tag] = np.load(f)
+    for k in "vnaos":
+        assert np.array_equal(outs["par"][k], outs["ser"][k]), k
+
+
 # ------------------------------------------------------------------ options ------------------
 def test_reference_radius_mode(tess, gen, ob):
     pts = gen.uniform(20_000, 57)

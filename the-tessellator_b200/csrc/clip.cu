@@ -78,6 +78,23 @@ struct RegMask {
     }
 };
 
+// 64 slots: one 64-bit register pair, native 64-bit shifts instead of select chains
+template <>
+struct RegMask<2> {
+    unsigned long long m;
+    __device__ __forceinline__ void clear() { m = 0ull; }
+    __device__ __forceinline__ uint32_t word(int k) const { return (uint32_t)(m >> (32 * k)); }
+    __device__ __forceinline__ void set_word(int k, uint32_t v) { m = (m & ~(0xFFFFFFFFull << (32 * k))) | ((unsigned long long)v << (32 * k)); }
+    __device__ __forceinline__ bool test(uint32_t i) const { return (m >> i) & 1ull; }
+    __device__ __forceinline__ void set(uint32_t i) { m |= 1ull << i; }
+    __device__ __forceinline__ int alloc(int limit) {
+        const int slot = __ffsll((long long)~m) - 1;  // -1 when full
+        if (slot < 0 || slot >= limit) return -1;
+        m |= 1ull << slot;
+        return slot;
+    }
+};
+
 template <int NW>
 struct SmemMask {
     uint32_t* w;
@@ -133,6 +150,12 @@ struct WarpSmem {
     typename Cfg::EdgeWord edge[Cfg::EMAX];  // {next, flip, target, face}
     typename Cfg::Idx fstart[Cfg::FMAX];
     typename Cfg::Idx estack[Cfg::EMAX];     // free half-edge slots (LIFO, like pool.rs's free list)
+    typename Cfg::EdgeWord xlist[32];        // crossings of the current cut: {outside end, inside end, new vertex, copy flag}
+    // scratch of the warp-parallel cut (small configuration only)
+    typename Cfg::Idx olist[32];             // outgoing half-edges of the cut, one per crossed face
+    typename Cfg::Idx pred[32];              // crossing k -> the crossing that precedes it around the cut
+    typename Cfg::Idx vfree[32];             // first free vertex slots
+    uint8_t kof[Cfg::REG ? Cfg::EMAX : 4];   // outgoing half-edge slot -> crossing index
     // masks of the large configuration live here (1-word placeholders otherwise)
     uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
         m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
@@ -241,12 +264,214 @@ struct Mesh {
     }
 };
 
+constexpr int CUT_FALLBACK = 3;
+
+// ---------------------------------------------------------------------------------------------
+// Warp-parallel form of Polyhedron::cut_with_plane (polyhedron.rs:438-642) for the generic case:
+// no vertex lies on the plane (none is Incident).  Every face crossed by the plane then has exactly
+// one outgoing half-edge (Inside -> Outside, polyhedron.rs:491-503) and one re-entering half-edge
+// (Outside -> Inside, :529-544); the reference visits these faces one after the other
+// (`outgoing = flip(re-entering)`, :603-607).  Here one lane takes one crossed face:
+//   1. one sweep over the half-edge table finds the outgoing half-edges, the half-edges that die
+//      (both ends Outside) and the faces that keep at least one half-edge;
+//   2. each lane follows its face loop to the re-entering half-edge (:529-544);
+//   3. `flip(re-entering)` names the next crossed face: the lanes form the cyclic order of the
+//      reference's walk; if they do not form ONE cycle through all outgoing half-edges (possible
+//      only when rounding breaks convexity) the serial walk takes over;
+//   4. each lane creates its intersection vertex (:567-572), its bridge half-edge (:582-587) and
+//      the cap half-edge paired with it (:592-598), linked exactly as the serial walk links them.
+// The start edge of the cap face is the one of the reference's first crossing (the outgoing
+// half-edge whose flip has the lowest slot, :413-432), so anchors and summation orders — hence
+// areas and volumes — are identical to the serial walk's.
+// Returns 1 (cut), CUT_FALLBACK (let the serial walk decide) or -1 (table overflow).
+// ---------------------------------------------------------------------------------------------
+template <class Cfg>
+__device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& cnt_nv) {
+    using MeshT = Mesh<Cfg>;
+    using EW = typename Cfg::EdgeWord;
+    using Idx = typename Cfg::Idx;
+    WarpSmem<Cfg>* sm = M.sm;
+    const int lane = M.lane;
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // ---- 1. sweep the half-edge table ----------------------------------------------------------
+    const int n_pass = M.edge_passes();
+    if (n_pass > 8) return CUT_FALLBACK;
+    uint32_t K = 0;
+    uint32_t deadbits = 0;  // bit p: my half-edge of pass p dies
+    MaskT<Cfg, MeshT::NWF> fkeep;
+    fkeep.clear();
+    for (int p = 0; p < n_pass; ++p) {
+        const EW w = M.edge_of_pass(p);
+        bool is_out = false, dead = false, keep = false;
+        uint32_t face = 0;
+        if (!MeshT::e_is_free(w)) {
+            const uint32_t t = MeshT::e_tgt(w);
+            const uint32_t s = MeshT::e_tgt(sm->edge[MeshT::e_flip(w)]);
+            const bool tout = M.outside.test(t), sout = M.outside.test(s);
+            is_out = tout && !sout;  // source Inside (nothing is Incident)
+            dead = tout && sout;
+            keep = !dead;
+            face = MeshT::e_face(w);
+        }
+        const uint32_t om = __ballot_sync(FULL, is_out);
+        if (is_out) {
+            const uint32_t k = K + __popc(om & lt);
+            if (k < 32u) {
+                sm->olist[k] = (Idx)(32 * p + lane);
+                sm->kof[32 * p + lane] = (uint8_t)k;
+            }
+        }
+        K += __popc(om);
+        deadbits |= (dead ? 1u : 0u) << p;
+#pragma unroll
+        for (int q = 0; q < MeshT::NWF; ++q) {
+            const uint32_t bits = (keep && (face >> 5) == (uint32_t)q) ? (1u << (face & 31u)) : 0u;
+            fkeep.set_word(q, fkeep.word(q) | __reduce_or_sync(FULL, bits));
+        }
+    }
+    if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
+    __syncwarp();
+
+    // ---- 2. one lane per crossed face: find the re-entering half-edge ---------------------------
+    const bool act = (uint32_t)lane < K;
+    uint32_t o = 0, f = 0, r = 0, pv = 0, cv = 0, so = 0, fo = 0xFFFFu;
+    EW wo = 0;
+    bool ok = true;
+    if (act) {
+        o = sm->olist[lane];
+        wo = sm->edge[o];
+        f = MeshT::e_face(wo);
+        fo = MeshT::e_flip(wo);
+        pv = MeshT::e_tgt(wo);  // previous_vertex_index (:491), Outside
+        r = MeshT::e_next(wo);  // :506
+        EW wc = sm->edge[r];
+        cv = MeshT::e_tgt(wc);
+        int budget = Cfg::EMAX;
+        while (!M.inside.test(cv) && --budget > 0) {  // :529-544
+            pv = cv;
+            r = MeshT::e_next(wc);
+            wc = sm->edge[r];
+            cv = MeshT::e_tgt(wc);
+        }
+        ok = budget > 0;
+        so = MeshT::e_flip(wc);  // the next crossed face's outgoing half-edge (:603-607)
+    }
+    // ---- 3. cyclic order of the crossings ------------------------------------------------------
+    uint32_t ks = 0;
+    if (act) {
+        ks = sm->kof[so];
+        ok = ok && ks < K && sm->olist[ks] == (Idx)so;
+        if (ok) sm->pred[ks] = (Idx)lane;
+    }
+    if (!__all_sync(FULL, ok)) return CUT_FALLBACK;
+    __syncwarp();
+    // the reference's first crossing: outgoing half-edge whose flip has the lowest slot (:413-432)
+    const uint32_t k0 = __reduce_min_sync(FULL, (fo << 8) | (uint32_t)lane) & 0xFFu;
+    uint32_t wi = 0;  // position of my crossing in the reference's walk order (k0 is 0)
+    {
+        uint32_t cur = k0, n = 0;
+        do {
+            if ((uint32_t)lane == cur) wi = n;
+            cur = __shfl_sync(FULL, ks, (int)cur);
+            ++n;
+        } while (cur != k0 && n < K);
+        if (cur != k0 || n != K) return CUT_FALLBACK;  // more than one cycle: not a convex cut
+    }
+    // ---- capacity: K vertices, 2K half-edges, one face ------------------------------------------
+    {
+        int vfree_n = 0;
+#pragma unroll
+        for (int p = 0; p < MeshT::NWV; ++p) vfree_n += 32 - __popc(M.vlive.word(p));
+        const int efree_n = M.e_top + (Cfg::E_LIMIT - M.e_hwm);
+        if ((int)K > vfree_n || 2 * (int)K > efree_n) return -1;
+    }
+    const int cap_face = M.flive.alloc(Cfg::FMAX);
+    if (cap_face < 0) return -1;
+    // first free vertex slots, in ascending order (what repeated lowest-free-bit allocation yields)
+    {
+        uint32_t base = 0;
+#pragma unroll
+        for (int p = 0; p < MeshT::NWV; ++p) {
+            const uint32_t fr = ~M.vlive.word(p);
+            if ((fr >> lane) & 1u) {
+                const uint32_t rk = base + __popc(fr & lt);
+                if (rk < 32u) sm->vfree[rk] = (Idx)(32 * p + lane);
+            }
+            base += __popc(fr);
+        }
+    }
+    __syncwarp();
+    // ---- 4. new vertex, bridge and cap half-edge of every crossing ------------------------------
+    // slots are handed out exactly as the serial walk would: it pops cap_first, then per crossing
+    // a bridge and (from the second crossing on) a cap half-edge; vertices by lowest free slot.
+    auto pop_slot = [&](int j) -> uint32_t { return j < M.e_top ? (uint32_t)sm->estack[M.e_top - 1 - j] : (uint32_t)(M.e_hwm + (j - M.e_top)); };
+    uint32_t nv = 0, ck = 0, br = 0;
+    if (act) {
+        nv = sm->vfree[wi];
+        ck = pop_slot(wi == 0u ? 0 : 2 * (int)wi + 1);
+        br = pop_slot(wi == 0u ? 1 : 2 * (int)wi);
+    }
+    const uint32_t pk = act ? (uint32_t)sm->pred[lane] : 0u;
+    const uint32_t nv_pred = __shfl_sync(FULL, nv, (int)pk);  // previous_intersection (:550, :600)
+    const uint32_t ck_pred = __shfl_sync(FULL, ck, (int)pk);
+    const uint32_t ck0 = __shfl_sync(FULL, ck, (int)k0);
+    uint32_t nb_lo = 0, nb_hi = 0;
+    if (act) {
+        const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
+        const Vec3 b = {sm->vx[cv], sm->vy[cv], sm->vz[cv]};
+        const Vec3 x = intersection(pl, a, b);  // :567-572 (a = outside end, b = inside end)
+        sm->vx[nv] = x.x;
+        sm->vy[nv] = x.y;
+        sm->vz[nv] = x.z;
+        sm->edge[br] = MeshT::pack(r, ck, nv, f);                     // bridge (:582-587)
+        sm->edge[ck] = MeshT::pack(ck_pred, br, nv_pred, (uint32_t)cap_face);  // cap edge (:592-598 / D6)
+        sm->edge[o] = MeshT::pack(br, fo, nv_pred, f);                // :550 + :590
+        sm->fstart[f] = (Idx)o;                                       // :578-580
+        if (nv < 32u) nb_lo = 1u << nv; else nb_hi = 1u << (nv - 32u);
+    }
+    if (lane == 0) {
+        sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (:479-482)
+        sm->fstart[cap_face] = (Idx)ck0;
+    }
+    // allocator state after 2K pops
+    {
+        const int pops = 2 * (int)K;
+        const int from_stack = pops < M.e_top ? pops : M.e_top;
+        M.e_hwm += pops - from_stack;
+        M.e_top -= from_stack;
+    }
+    __syncwarp();
+    // ---- retire: Outside vertices, dead half-edges (ascending slot order), faces without edges ----
+    nb_lo = __reduce_or_sync(FULL, nb_lo);
+    nb_hi = __reduce_or_sync(FULL, nb_hi);
+    M.vlive.set_word(0, (M.vlive.word(0) & ~M.outside.word(0)) | nb_lo);
+    if (MeshT::NWV > 1) M.vlive.set_word(1, (M.vlive.word(1) & ~M.outside.word(1)) | nb_hi);
+    const int old_top = M.e_top;
+    for (int p = 0; p < n_pass; ++p) {
+        const bool dead = (deadbits >> p) & 1u;
+        const uint32_t dm = __ballot_sync(FULL, dead);
+        if (dead) sm->estack[M.e_top + __popc(dm & lt)] = (Idx)(32 * p + lane);
+        M.e_top += __popc(dm);
+    }
+    __syncwarp();
+    for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
+#pragma unroll
+    for (int q = 0; q < MeshT::NWF; ++q) {
+        const uint32_t capbit = ((uint32_t)cap_face >> 5) == (uint32_t)q ? (1u << (cap_face & 31)) : 0u;
+        M.flive.set_word(q, (M.flive.word(q) & fkeep.word(q)) | capbit);
+    }
+    cnt_nv += K;
+    __syncwarp();
+    return 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One plane against the mesh: Polyhedron::cut_with_plane (polyhedron.rs:438-642).
 // Returns 0 = no cut, 1 = cut, 2 = skipped (D17), <0 = capacity overflow / inconsistency.
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv) {
+__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv, bool serial_only) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
     WarpSmem<Cfg>* sm = M.sm;
@@ -254,7 +479,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 
     // ---- classify every live vertex (find_outgoing_edge's vertex scan, polyhedron.rs:399-405,
     //      and every later vector_location call of the walk) --------------------------------------
-    uint32_t any_out = 0;
+    uint32_t any_out = 0, any_incident = 0;
     uint32_t nlive = 0;
 #pragma unroll
     for (int p = 0; p < MeshT::NWV; ++p) {
@@ -274,10 +499,19 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         M.inside.set_word(p, in);
         M.outside.set_word(p, out);
         any_out |= out;
+        any_incident |= lw & ~in & ~out;
         nlive += __popc(lw);
     }
     cnt_vc += nlive;
     if (!any_out) return 0;  // polyhedron.rs:408-410
+
+    // ---- fast path: no vertex on the plane -> the whole cut in lane-parallel form ----------------
+    if constexpr (Cfg::REG) {
+        if (!any_incident && !serial_only) {
+            const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv);
+            if (rc != CUT_FALLBACK) return rc;
+        }
+    }
 
     // ---- first edge (slot order) with target Inside whose flip's target is Outside; the walk
     //      starts on the flip (polyhedron.rs:413-432) ---------------------------------------------
@@ -311,8 +545,30 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     uint32_t out_e = (uint32_t)first;
     uint32_t prev_int = Cfg::NONE;  // previous_intersection
     uint32_t cap_prev = (uint32_t)cap_first;
-    int nbridge = 0;
-    int guard = 0;
+    uint32_t nbridge = 0;
+    int budget = 2 * Cfg::EMAX;  // a consistent mesh cannot need more steps
+
+    // The walk touches topology only.  Each crossing is recorded in sm->xlist and its vertex
+    // (Plane::intersection, or the copy of an Incident vertex) is computed afterwards, one lane per
+    // crossing: coordinates of NEW vertices are never read while walking.
+    auto emit_vertices = [&](uint32_t count) {
+        __syncwarp();
+        if ((uint32_t)lane < count) {
+            const EW rec = sm->xlist[lane];
+            const uint32_t pv = MeshT::e_next(rec), cv = MeshT::e_flip(rec), nv = MeshT::e_tgt(rec);
+            const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
+            Vec3 x = a;  // previous vertex Incident: plain copy (polyhedron.rs:555-565)
+            if (MeshT::e_face(rec) == 0u) {
+                const Vec3 b = {sm->vx[cv], sm->vy[cv], sm->vz[cv]};
+                x = intersection(pl, a, b);  // :567-572 (a = outside end, b = inside end)
+            }
+            sm->vx[nv] = x.x;
+            sm->vy[nv] = x.y;
+            sm->vz[nv] = x.z;
+        }
+        __syncwarp();
+    };
+
     do {
         const EW w_out = sm->edge[out_e];
         uint32_t pv = MeshT::e_tgt(w_out);  // previous_vertex_index (:491)
@@ -328,28 +584,16 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             cur_e = MeshT::e_next(w_cur);
             w_cur = sm->edge[cur_e];
             cv = MeshT::e_tgt(w_cur);
-            if (++guard > Cfg::EMAX) {
+            if (--budget < 0) {
                 status |= ST_INCONSISTENT;
                 return -2;
             }
         }
-        M.set_field(out_e, 2, prev_int);  // :550
-        if (need) {                       // :552-601
+        if (need) {  // :552-601
             const int nv = M.vlive.alloc(Cfg::VMAX);
             const int br = M.alloc_edge();
             if (nv < 0 || br < 0) return -1;
-            Vec3 x;
-            const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
-            if (M.outside.test(pv)) {
-                const Vec3 b = {sm->vx[cv], sm->vy[cv], sm->vz[cv]};
-                x = intersection(pl, a, b);  // :567-572 (a = outside end, b = inside end)
-            } else {
-                x = a;  // previous vertex Incident: plain copy (:555-565)
-            }
-            sm->vx[nv] = x.x;
-            sm->vy[nv] = x.y;
-            sm->vz[nv] = x.z;
-            cnt_nv += 1;
+            sm->xlist[nbridge & 31u] = MeshT::pack(pv, cv, (uint32_t)nv, M.outside.test(pv) ? 0u : 1u);
             const uint32_t f = MeshT::e_face(w_out);
             sm->fstart[f] = (typename Cfg::Idx)out_e;  // :578-580
             uint32_t capk;
@@ -364,18 +608,23 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
                 capk = (uint32_t)ce;
                 sm->edge[capk] = MeshT::pack(cap_prev, (uint32_t)br, prev_int, (uint32_t)cap_face);
             }
-            sm->edge[br] = MeshT::pack(cur_e, capk, (uint32_t)nv, f);  // :582-587
-            M.set_field(out_e, 0, (uint32_t)br);                        // :590
+            sm->edge[br] = MeshT::pack(cur_e, capk, (uint32_t)nv, f);                     // :582-587
+            sm->edge[out_e] = MeshT::pack((uint32_t)br, MeshT::e_flip(w_out), prev_int, f);  // :550 + :590
             cap_prev = capk;
             prev_int = (uint32_t)nv;
             ++nbridge;
+            if ((nbridge & 31u) == 0u) emit_vertices(32u);
+        } else {
+            M.set_field(out_e, 2, prev_int);  // :550
         }
         out_e = MeshT::e_flip(w_cur);  // :603-607
-        if (++guard > Cfg::EMAX) {
+        if (--budget < 0) {
             status |= ST_INCONSISTENT;
             return -2;
         }
     } while (out_e != (uint32_t)first);  // :620-622
+    if (nbridge & 31u) emit_vertices(nbridge & 31u);
+    cnt_nv += nbridge;
 
     // close the loop: first outgoing edge and first cap edge end at the last intersection
     M.set_field((uint32_t)first, 2, prev_int);
@@ -606,7 +855,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams 
                     pl.off = __shfl_sync(FULL, mypl.off, l);
                     const long long nid = __shfl_sync(FULL, cid, l);
                     c_test += 1;
-                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv);
+                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u);
                     if (rc < 0) {
                         if (rc == -1) status |= ST_CAPACITY_OVERFLOW;
                         failed = true;

@@ -83,6 +83,7 @@ struct ClipParams {
     uint32_t* n_failed;
     uint32_t failed_cap;
     uint32_t mark_large;           // OR ST_LARGE_PATH into the status of every row written
+    uint32_t flags;                // bit 0: serial walk only (TESS_FORCE_SERIAL=1, for A/B checks)
 };
 
 #define TESS_CUDA_CHECK(expr)                                                                      \
