@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtess_b200.so")
+LIB_PATH = os.environ.get("TESS_LIB_PATH") or os.path.join(_HERE, "libtess_b200.so")  # override: A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tess.h")
 

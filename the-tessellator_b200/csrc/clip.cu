@@ -122,7 +122,11 @@ struct SmemMask {
 // ---------------------------------------------------------------------------------------------
 // Configurations
 // ---------------------------------------------------------------------------------------------
+#ifndef TESS_CLIP_MINBLOCKS
+#define TESS_CLIP_MINBLOCKS 5  // resident CTAs per SM the small kernel is compiled for (register cap)
+#endif
 struct SmallCfg {
+    static constexpr int MINB = TESS_CLIP_MINBLOCKS;
     static constexpr int VMAX = 64, EMAX = 256, FMAX = 64;
     static constexpr int E_LIMIT = 255;  // slot 255 is the "none" marker of 8-bit ids
     static constexpr int WARPS = 4;
@@ -133,6 +137,7 @@ struct SmallCfg {
     static constexpr int SHIFT = 8;
 };
 struct LargeCfg {
+    static constexpr int MINB = 1;
     static constexpr int VMAX = 1024, EMAX = 3072, FMAX = 512;
     static constexpr int E_LIMIT = 3072;
     static constexpr int WARPS = 1;
@@ -299,8 +304,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     if (n_pass > 8) return CUT_FALLBACK;
     uint32_t K = 0;
     uint32_t deadbits = 0;  // bit p: my half-edge of pass p dies
-    MaskT<Cfg, MeshT::NWF> fkeep;
-    fkeep.clear();
+    uint32_t keep_lo = 0, keep_hi = 0;  // faces my surviving half-edges belong to (FMAX <= 64 here)
     for (int p = 0; p < n_pass; ++p) {
         const EW w = M.edge_of_pass(p);
         bool is_out = false, dead = false, keep = false;
@@ -324,10 +328,8 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         }
         K += __popc(om);
         deadbits |= (dead ? 1u : 0u) << p;
-#pragma unroll
-        for (int q = 0; q < MeshT::NWF; ++q) {
-            const uint32_t bits = (keep && (face >> 5) == (uint32_t)q) ? (1u << (face & 31u)) : 0u;
-            fkeep.set_word(q, fkeep.word(q) | __reduce_or_sync(FULL, bits));
+        if (keep) {
+            if (face < 32u) keep_lo |= 1u << face; else keep_hi |= 1u << (face - 32u);
         }
     }
     if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
@@ -368,15 +370,23 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     __syncwarp();
     // the reference's first crossing: outgoing half-edge whose flip has the lowest slot (:413-432)
     const uint32_t k0 = __reduce_min_sync(FULL, (fo << 8) | (uint32_t)lane) & 0xFFu;
-    uint32_t wi = 0;  // position of my crossing in the reference's walk order (k0 is 0)
+    // position of my crossing in the reference's walk order (k0 is 0): list ranking by pointer
+    // jumping — after ceil(log2 K) rounds every lane of k0's cycle knows its distance to k0
+    uint32_t wi = 0;
     {
-        uint32_t cur = k0, n = 0;
-        do {
-            if ((uint32_t)lane == cur) wi = n;
-            cur = __shfl_sync(FULL, ks, (int)cur);
-            ++n;
-        } while (cur != k0 && n < K);
-        if (cur != k0 || n != K) return CUT_FALLBACK;  // more than one cycle: not a convex cut
+        const bool term = !act || (uint32_t)lane == k0;
+        uint32_t nxt = term ? k0 : ks, d = term ? 0u : 1u;
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+            if ((1u << step) >= K) break;
+            const uint32_t d2 = __shfl_sync(FULL, d, (int)nxt);
+            const uint32_t n2 = __shfl_sync(FULL, nxt, (int)nxt);
+            d += d2;
+            nxt = n2;
+        }
+        // succ is a permutation of the crossings (flip is a bijection): everyone reaches k0 <=> one cycle
+        if (__any_sync(FULL, act && nxt != k0)) return CUT_FALLBACK;  // not a convex cut
+        wi = ((uint32_t)lane == k0) ? 0u : K - d;
     }
     // ---- capacity: K vertices, 2K half-edges, one face ------------------------------------------
     {
@@ -447,20 +457,23 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     nb_hi = __reduce_or_sync(FULL, nb_hi);
     M.vlive.set_word(0, (M.vlive.word(0) & ~M.outside.word(0)) | nb_lo);
     if (MeshT::NWV > 1) M.vlive.set_word(1, (M.vlive.word(1) & ~M.outside.word(1)) | nb_hi);
-    const int old_top = M.e_top;
-    for (int p = 0; p < n_pass; ++p) {
-        const bool dead = (deadbits >> p) & 1u;
-        const uint32_t dm = __ballot_sync(FULL, dead);
-        if (dead) sm->estack[M.e_top + __popc(dm & lt)] = (Idx)(32 * p + lane);
-        M.e_top += __popc(dm);
+    if (__any_sync(FULL, deadbits != 0u)) {
+        const int old_top = M.e_top;
+        for (int p = 0; p < n_pass; ++p) {
+            const bool dead = (deadbits >> p) & 1u;
+            const uint32_t dm = __ballot_sync(FULL, dead);
+            if (dead) sm->estack[M.e_top + __popc(dm & lt)] = (Idx)(32 * p + lane);
+            M.e_top += __popc(dm);
+        }
+        __syncwarp();
+        for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
+        // a face can only lose all its half-edges when some half-edge died
+        keep_lo = __reduce_or_sync(FULL, keep_lo);
+        keep_hi = __reduce_or_sync(FULL, keep_hi);
+        M.flive.set_word(0, M.flive.word(0) & keep_lo);
+        if (MeshT::NWF > 1) M.flive.set_word(1, M.flive.word(1) & keep_hi);
     }
-    __syncwarp();
-    for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
-#pragma unroll
-    for (int q = 0; q < MeshT::NWF; ++q) {
-        const uint32_t capbit = ((uint32_t)cap_face >> 5) == (uint32_t)q ? (1u << (cap_face & 31)) : 0u;
-        M.flive.set_word(q, (M.flive.word(q) & fkeep.word(q)) | capbit);
-    }
+    M.flive.set((uint32_t)cap_face);
     cnt_nv += K;
     __syncwarp();
     return 1;
@@ -721,7 +734,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 // ---------------------------------------------------------------------------------------------
 // COUNT: also accumulate the work counters (a separate instantiation keeps them out of the timed kernel).
 template <class Cfg, bool COUNT>
-__global__ void __launch_bounds__(Cfg::WARPS * 32) clip_kernel(const ClipParams P) {
+__global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const ClipParams P) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
     extern __shared__ __align__(16) unsigned char smem_raw[];
