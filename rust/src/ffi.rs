@@ -1,0 +1,50 @@
+//! 1:1 declarations of include/tess.h.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct tess_diagram {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct tess_result {
+    _private: [u8; 0],
+}
+
+pub const TESS_OK: c_int = 0;
+pub const TESS_F64: c_int = 0;
+pub const TESS_OUT_VOLUME: u32 = 1;
+pub const TESS_OUT_NEIGHBORS: u32 = 2;
+pub const TESS_OUT_AREAS: u32 = 4;
+pub const TESS_OUT_VERTICES: u32 = 8;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct tess_opts {
+    pub search_radius: f64,
+    pub target_group: i64,
+    pub outputs: u32,
+    pub table_radius: i32,
+    pub stream: *mut c_void,
+}
+
+extern "C" {
+    pub fn tess_last_error() -> *const c_char;
+    pub fn tess_opts_default(o: *mut tess_opts);
+    pub fn tess_diagram_create(out: *mut *mut tess_diagram, real_type: c_int, device: c_int) -> c_int;
+    pub fn tess_diagram_destroy(d: *mut tess_diagram);
+    pub fn tess_diagram_add_particles(d: *mut tess_diagram, xyz: *const c_void, n: usize, stride_bytes: usize, groups: *const u64, stream: *mut c_void) -> c_int;
+    pub fn tess_diagram_initialize(d: *mut tess_diagram, box6: *const f64, stream: *mut c_void) -> c_int;
+    pub fn tess_diagram_grid_info(d: *const tess_diagram, n_points: *mut u64, cpd: *mut u64, bounds: *mut f64, sizes: *mut f64, inv_sizes: *mut f64) -> c_int;
+    pub fn tess_compute_all(d: *const tess_diagram, opts: *const tess_opts, out: *mut *mut tess_result) -> c_int;
+    pub fn tess_compute_at_points(d: *const tess_diagram, xyz: *const f64, m: usize, opts: *const tess_opts, out: *mut *mut tess_result) -> c_int;
+    pub fn tess_result_free(r: *mut tess_result);
+    pub fn tess_result_n_cells(r: *const tess_result, n_cells: *mut u64, n_faces: *mut u64) -> c_int;
+    pub fn tess_result_volumes(r: *mut tess_result, out: *mut *const f64) -> c_int;
+    pub fn tess_result_face_offsets(r: *mut tess_result, out: *mut *const u64) -> c_int;
+    pub fn tess_result_neighbors(r: *mut tess_result, out: *mut *const i64) -> c_int;
+    pub fn tess_result_areas(r: *mut tess_result, out: *mut *const f64) -> c_int;
+    pub fn tess_result_status(r: *mut tess_result, out: *mut *const u32) -> c_int;
+    pub fn tess_result_vertex_offsets(r: *mut tess_result, out: *mut *const u64) -> c_int;
+    pub fn tess_result_vertices(r: *mut tess_result, out: *mut *const f64) -> c_int;
+}

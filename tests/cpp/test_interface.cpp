@@ -1,0 +1,62 @@
+// C++ harness over include/tess.hpp: the reference's usage pattern (interface.rs) end to end.
+// Built and run by tests/test_gpu_cpp_mirror.py on the GPU box.  Prints one line per cell checked;
+// the Python side compares the numbers with the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+
+#include "tess.hpp"
+
+// a user point type exposing the ToCeleryPoint getters (celery.rs:56-60)
+struct MyParticle {
+    double px, py, pz;
+    int payload;
+    double get_x() const { return px; }
+    double get_y() const { return py; }
+    double get_z() const { return pz; }
+};
+
+static uint64_t mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static double u01(uint64_t seed, uint64_t i, uint64_t c) { return (double)(mix(mix(seed) + 3 * i + c) >> 11) * 0x1.0p-53; }
+
+int main(int argc, char** argv) {
+    const size_t n = argc > 1 ? std::strtoull(argv[1], nullptr, 10) : 3000;
+    try {
+        tess::Diagram diagram;  // Diagram::default()
+        for (size_t i = 0; i < n; ++i) diagram.add_particle_with_group(MyParticle{u01(62, i, 0), u01(62, i, 1), u01(62, i, 2), (int)i}, 0);
+        const tess::Polyhedron box{0, 0, 0, 1, 1, 1};  // Polyhedron::new(0,0,0,1,1,1)
+        diagram.initialize(box);
+        double total = 0;
+        for (size_t i = 0; i < n; ++i) {
+            tess::Cell cell = diagram.get_cell_at_index(i, box, std::nullopt, std::nullopt);
+            cell.compute_voronoi_cell();
+            const double v = cell.compute_volume();
+            total += v;
+            if (i % 500 == 7) {
+                std::printf("cell %zu volume %.17g faces", i, v);
+                for (const tess::VoronoiFace& f : cell.compute_faces()) std::printf(" %lld:%.17g", (long long)f.compute_neighbor(), f.compute_area());
+                std::printf("\n");
+            }
+        }
+        std::printf("total %.17g\n", total);
+        // a cell around a point that is not a particle (interface.rs:211-232)
+        tess::Cell q = diagram.get_cell_at_particle(tess::Vector3{0.31, 0.62, 0.44}, box);
+        std::printf("query volume %.17g nfaces %zu\n", q.compute_volume(), q.compute_neighbors().size());
+        // error behaviour: wrong start polyhedron, add after initialize
+        try {
+            diagram.get_cell_at_index(0, tess::Polyhedron{0, 0, 0, 2, 2, 2});
+            std::printf("ERROR: foreign polyhedron accepted\n");
+            return 2;
+        } catch (const tess::Error& e) {
+            std::printf("expected error %d\n", e.code);
+        }
+    } catch (const std::exception& e) {
+        std::printf("FAILED: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
