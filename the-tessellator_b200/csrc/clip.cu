@@ -161,6 +161,9 @@ struct WarpSmem {
     typename Cfg::Idx pred[32];              // crossing k -> the crossing that precedes it around the cut
     typename Cfg::Idx vfree[32];             // first free vertex slots
     uint8_t kof[Cfg::REG ? Cfg::EMAX : 4];   // outgoing half-edge slot -> crossing index
+    // candidate tile: bisector plane {n, offset} and id of the candidate each lane staged
+    double4 cand_plane[32];
+    long long cand_id[32];
     // masks of the large configuration live here (1-word placeholders otherwise)
     uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
         m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
@@ -850,9 +853,13 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 }
                 uint32_t uncounted = __ballot_sync(FULL, has && !src_marker);  // C_vis bookkeeping
                 // bisector plane of every candidate that can still matter (Plane::halfway_from_origin_to)
-                Plane mypl = {0, 0, 0, 0};
                 const bool cand = (has && src_marker) || (adm && r2 < rej_thr);
-                if (cand && !src_marker) mypl = halfway_from_origin_to(Vec3{rx, ry, rz});
+                if (cand && !src_marker) {
+                    const Plane mypl = halfway_from_origin_to(Vec3{rx, ry, rz});
+                    sm->cand_plane[lane] = make_double4(mypl.nx, mypl.ny, mypl.nz, mypl.off);
+                    sm->cand_id[lane] = cid;
+                }
+                __syncwarp();
                 uint32_t pending = __ballot_sync(FULL, cand && !(src_key > stop_thr));
                 while (pending) {
                     const int l = __ffs(pending) - 1;
@@ -861,12 +868,9 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                         status |= ST_HALO_INSUFFICIENT;
                         continue;
                     }
-                    Plane pl;
-                    pl.nx = __shfl_sync(FULL, mypl.nx, l);
-                    pl.ny = __shfl_sync(FULL, mypl.ny, l);
-                    pl.nz = __shfl_sync(FULL, mypl.nz, l);
-                    pl.off = __shfl_sync(FULL, mypl.off, l);
-                    const long long nid = __shfl_sync(FULL, cid, l);
+                    const double4 pq = sm->cand_plane[l];  // broadcast read
+                    const Plane pl = {pq.x, pq.y, pq.z, pq.w};
+                    const long long nid = sm->cand_id[l];
                     c_test += 1;
                     const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u);
                     if (rc < 0) {
