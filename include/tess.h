@@ -164,6 +164,25 @@ int tess_result_download(const tess_result* r, double* volumes, uint64_t* face_o
 /* Device views for callers that keep results on the GPU (any pointer may be NULL). */
 int tess_result_device_views(const tess_result* r, const double** volumes, const uint64_t** face_offsets, const int64_t** neighbors, const double** areas, const uint32_t** status, const int64_t** cell_ids);
 
+/* ---- Radius queries on the grid (celery.rs:753-855, 1023-1075; interface.rs:348-365) --------- */
+
+typedef struct tess_query tess_query;
+enum {
+    TESS_QUERY_CELL_RADIUS = 0,    /* Celery::find_neighbors_in_cell_radius (celery.rs:802): every particle of every grid
+                                      cell within `radius` of the query's cell (adjacent cells count as distance 0) */
+    TESS_QUERY_REAL_RADIUS = 1,    /* Celery::find_neighbors_in_real_radius (celery.rs:825): additionally |p - q|^2 <= r^2 */
+    TESS_QUERY_NEIGHBOR_CLOUD = 2  /* ExpandingSearch::expand_all_in_radius (celery.rs:1023) as used by
+                                      Cell::compute_neighbor_cloud (interface.rs:348): search-table order, stops at the first
+                                      entry whose squared key exceeds `radius`; target_group filters (interface.rs:359) */
+};
+/* m query positions (host, packed f64 triples) -> CSR lists of particle ids in the reference's order.
+ * Whole-domain diagrams only. */
+int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, void* stream, tess_query** out);
+void tess_query_free(tess_query* q);
+int tess_query_offsets(tess_query* q, const uint64_t** out);  /* m+1 */
+int tess_query_indices(tess_query* q, const int64_t** out);   /* offsets[m] particle ids */
+int tess_query_status(tess_query* q, const uint32_t** out);   /* m; TESS_STATUS_TABLE_EXHAUSTED cannot occur: the table is sized for the radius */
+
 /* ---- Slab partition helpers (multi-GPU; the collectives themselves are the caller's) ------ */
 
 /* Histogram of particles per global grid x-plane: counts_dev[cpd] (u64, device, zeroed by the call). */

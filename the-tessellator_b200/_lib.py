@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tess.h")
 
 TESS_F64, TESS_F32 = 0, 1
+QUERY_CELL_RADIUS, QUERY_REAL_RADIUS, QUERY_NEIGHBOR_CLOUD = 0, 1, 2
 OUT_VOLUME, OUT_NEIGHBORS, OUT_AREAS, OUT_VERTICES, OUT_COUNTERS = 1, 2, 4, 8, 16
 STATUS_DEGENERATE_SKIP, STATUS_TABLE_EXHAUSTED, STATUS_CAPACITY_OVERFLOW, STATUS_HALO_INSUFFICIENT, STATUS_INCONSISTENT = 1, 2, 4, 8, 16
 COUNTER_NAMES = ("visited", "tested", "vertex_classifications", "cuts", "new_vertices", "table_entries", "degenerate_skips", "faces")
@@ -30,6 +31,7 @@ SYMBOLS = (
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
     "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs",
+    "tess_find_neighbors", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
     "tess_result_download", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
 
@@ -122,6 +124,10 @@ def lib() -> C.CDLL:
     sig("tess_result_volume_sum", ci, vp, P(f64))
     sig("tess_result_device_views", ci, vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(vp))
     sig("tess_result_download", ci, vp, vp, vp, vp, vp, vp, vp)
+    sig("tess_find_neighbors", ci, vp, vp, sz, f64, ci, i64, vp, P(vp))
+    sig("tess_query_free", None, vp)
+    for n in ("tess_query_offsets", "tess_query_indices", "tess_query_status"):
+        sig(n, ci, vp, P(vp))
     sig("tess_kernel_launch_count", u64)
     sig("tess_result_timings", ci, vp, P(f64 * 4))
     sig("tess_diagram_timings", ci, vp, P(f64 * 1))

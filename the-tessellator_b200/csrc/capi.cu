@@ -916,6 +916,105 @@ int tess_result_device_views(const tess_result* r, const double** volumes, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// radius queries
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct tess_query {
+    std::vector<uint64_t> offsets;
+    std::vector<int64_t> indices;
+    std::vector<uint32_t> status;
+};
+
+extern "C" {
+
+int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, void* stream, tess_query** out) {
+    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "radius queries need a whole-domain diagram");
+    if (mode < 0 || mode > 2) return fail(TESS_ERR_INVALID, "bad query mode");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    std::unique_ptr<tess_query> q(new tess_query());
+    q->offsets.assign(m + 1, 0);
+    q->status.assign(m, 0);
+    if (m == 0) {
+        *out = q.release();
+        return TESS_OK;
+    }
+    Scratch tmp(s);
+    double* qx = tmp.get<double>(3 * m);
+    uint32_t* counts = tmp.get<uint32_t>(m + 1);
+    uint32_t* flags = tmp.get<uint32_t>(m);
+    uint64_t* offs = tmp.get<uint64_t>(m + 1);
+    void* scan_tmp = tmp.get<char>(scan_tmp_bytes(m + 1));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(qx, xyz, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (m + 1), s));
+    QueryParams Q{};
+    Q.sorted = d->sorted.as<Particle>();
+    Q.delim = d->delim.as<uint32_t>();
+    Q.groups_sorted = d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr;
+    Q.grid = d->grid;
+    Q.xyz = qx;
+    Q.n_query = m;
+    Q.radius = radius;
+    Q.mode = mode;
+    Q.target_group = target_group;
+    Q.counts = counts;
+    Q.flags = flags;
+    if (mode == TESS_QUERY_NEIGHBOR_CLOUD) {
+        // the table must hold every entry with key <= radius: (R*size)^2 > radius on every axis
+        const double smin = std::min(d->grid.sx, std::min(d->grid.sy, d->grid.sz));
+        int R = static_cast<int>(d->grid.cpd);  // full table
+        if (radius >= 0 && smin > 0) {
+            const double need = std::sqrt(radius) / smin + 2.0;
+            if (need < static_cast<double>(d->grid.cpd)) R = std::max(1, static_cast<int>(need));
+        }
+        const ShellTable& t = d->table(R, s);
+        Q.table = t.dev.as<ShellEntry>();
+        Q.table_len = t.len;
+        Q.table_full = t.full ? 1u : 0u;
+    }
+    launch_radius_query(Q, /*fill=*/false, s);
+    launch_exclusive_scan_u32_to_u64(counts, offs, m + 1, scan_tmp, scan_tmp_bytes(m + 1), s);
+    TESS_CUDA_CHECK(cudaMemcpyAsync(q->offsets.data(), offs, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(q->status.data(), flags, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    const uint64_t total = q->offsets[m];
+    q->indices.resize(total);
+    if (total) {
+        int64_t* idx = tmp.get<int64_t>(total);
+        Q.offsets = offs;
+        Q.indices = idx;
+        launch_radius_query(Q, /*fill=*/true, s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(q->indices.data(), idx, sizeof(int64_t) * total, cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    *out = q.release();
+    return TESS_OK;
+    TESS_CATCH
+}
+
+void tess_query_free(tess_query* q) { delete q; }
+int tess_query_offsets(tess_query* q, const uint64_t** out) {
+    if (!q || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = q->offsets.data();
+    return TESS_OK;
+}
+int tess_query_indices(tess_query* q, const int64_t** out) {
+    if (!q || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = q->indices.data();
+    return TESS_OK;
+}
+int tess_query_status(tess_query* q, const uint32_t** out) {
+    if (!q || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = q->status.data();
+    return TESS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // slab helpers
 // ------------------------------------------------------------------------------------------------
 int tess_bounds(const double* xyz_dev, size_t n, double* bounds_dev, void* stream) {

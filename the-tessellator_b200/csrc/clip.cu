@@ -164,6 +164,7 @@ struct WarpSmem {
     // candidate tile: bisector plane {n, offset} and id of the candidate each lane staged
     double4 cand_plane[32];
     long long cand_id[32];
+    double cpos[4];                          // position of the cell's particle (kept here, not in registers)
     // masks of the large configuration live here (1-word placeholders otherwise)
     uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
         m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
@@ -257,6 +258,7 @@ struct Mesh {
 #pragma unroll
         for (int p = 0; p < NWV; ++p) {
             const uint32_t lw = vlive.word(p);
+            if (lw == 0u) continue;
             if ((lw >> lane) & 1u) {
                 const int v = 32 * p + lane;
                 const double x = sm->vx[v], y = sm->vy[v], z = sm->vz[v];
@@ -501,7 +503,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     for (int p = 0; p < MeshT::NWV; ++p) {
         const uint32_t lw = M.vlive.word(p);
         M.vbefore.set_word(p, lw);
-        if (!Cfg::REG && lw == 0u) {
+        if (lw == 0u) {  // an empty word of slots (the upper half of a small cell, most of the time)
             M.inside.set_word(p, 0u);
             M.outside.set_word(p, 0u);
             continue;
@@ -759,34 +761,35 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         uint32_t c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0, c_deg = 0;  // this cell
 
         // ---- the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207) -----------
-        double px, py, pz;
         uint32_t self_slot = 0xFFFFFFFFu;
-        size_t row = work;
-        long long self_id = (long long)work;
-        if (P.query_xyz) {  // get_cell_at_particle (interface.rs:218-231): no self exclusion
-            px = P.query_xyz[3 * (size_t)work];
-            py = P.query_xyz[3 * (size_t)work + 1];
-            pz = P.query_xyz[3 * (size_t)work + 2];
-        } else {
-            self_slot = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
-            const double2* q = reinterpret_cast<const double2*>(P.sorted + self_slot);
-            const double2 a = __ldg(q), b = __ldg(q + 1);
-            px = a.x; py = a.y; pz = b.x;
-            self_id = __double_as_longlong(b.y);
-            row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
+        int hx, hy, hz;
+        {
+            double px, py, pz;
+            if (P.query_xyz) {  // get_cell_at_particle (interface.rs:218-231): no self exclusion
+                px = P.query_xyz[3 * (size_t)work];
+                py = P.query_xyz[3 * (size_t)work + 1];
+                pz = P.query_xyz[3 * (size_t)work + 2];
+            } else {
+                self_slot = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
+                const double2* q = reinterpret_cast<const double2*>(P.sorted + self_slot);
+                const double2 a = __ldg(q), b = __ldg(q + 1);
+                px = a.x; py = a.y; pz = b.x;
+            }
+            if (lane == 0) { sm->cpos[0] = px; sm->cpos[1] = py; sm->cpos[2] = pz; }
+            M.build_cube(P.box, px, py, pz);
+            // ExpandingSearch::new (celery.rs:882-902): home cell of the position
+            hx = (int)axis_index(px, G.xmin, G.xmax, G.ix, G.cpd);
+            hy = (int)axis_index(py, G.ymin, G.ymax, G.iy, G.cpd);
+            hz = (int)axis_index(pz, G.zmin, G.zmax, G.iz, G.cpd);
         }
-        const size_t srow = P.stage_by_work ? (size_t)work : row;
         uint32_t status = 0;
-        M.build_cube(P.box, px, py, pz);
-        double rmax2 = M.max_radius_sq();
+        const double rmax2 = M.max_radius_sq();
 
-        // ExpandingSearch::new (celery.rs:882-902): home cell of the position
-        const int hx = (int)axis_index(px, G.xmin, G.xmax, G.ix, G.cpd);
-        const int hy = (int)axis_index(py, G.ymin, G.ymax, G.iy, G.cpd);
-        const int hz = (int)axis_index(pz, G.zmin, G.zmax, G.iz, G.cpd);
 
+        // one threshold: security mode compares table keys AND |r|^2 with 4*max|v|^2; reference-radius
+        // mode compares table keys with the caller's radius (celery.rs:1036) and rejects nothing
         double stop_thr = radius_mode ? P.search_radius : mul(4.0, rmax2);
-        double rej_thr = radius_mode ? __longlong_as_double(0x7ff0000000000000LL) : stop_thr;
+#define rej_ok(r2_) (radius_mode || (r2_) < stop_thr)
         bool done = false;
         bool failed = false;
 
@@ -844,7 +847,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     const double2* cq = reinterpret_cast<const double2*>(P.sorted + slot);
                     const double2 a = __ldg(cq), b = __ldg(cq + 1);
                     // interface.rs:322-326: search point - position
-                    rx = subd(a.x, px); ry = subd(a.y, py); rz = subd(b.x, pz);
+                    rx = subd(a.x, sm->cpos[0]); ry = subd(a.y, sm->cpos[1]); rz = subd(b.x, sm->cpos[2]);
                     cid = __double_as_longlong(b.y);
                     r2 = dot3(rx, ry, rz, rx, ry, rz);
                     adm = slot != self_slot;  // interface.rs:283/301 (by index)
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 }
                 uint32_t uncounted = __ballot_sync(FULL, has && !src_marker);  // C_vis bookkeeping
                 // bisector plane of every candidate that can still matter (Plane::halfway_from_origin_to)
-                const bool cand = (has && src_marker) || (adm && r2 < rej_thr);
+                const bool cand = (has && src_marker) || (adm && rej_ok(r2));
                 if (cand && !src_marker) {
                     const Plane mypl = halfway_from_origin_to(Vec3{rx, ry, rz});
                     sm->cand_plane[lane] = make_double4(mypl.nx, mypl.ny, mypl.nz, mypl.off);
@@ -887,10 +890,8 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                             const uint32_t upto = uncounted & ((2u << l) - 1u);
                             c_vis += __popc(upto & __ballot_sync(FULL, !(src_key > stop_thr)));
                             uncounted &= ~upto;
-                            rmax2 = M.max_radius_sq();
-                            stop_thr = mul(4.0, rmax2);
-                            rej_thr = stop_thr;
-                            pending &= __ballot_sync(FULL, cand && !(src_key > stop_thr) && (src_marker || r2 < rej_thr));
+                            stop_thr = mul(4.0, M.max_radius_sq());
+                            pending &= __ballot_sync(FULL, cand && !(src_key > stop_thr) && (src_marker || rej_ok(r2)));
                         }
                     }
                 }
@@ -921,6 +922,14 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         for (int q = 0; q < MeshT::NWF; ++q) nf += __popc(M.flive.word(q));
         double vol_part = 0.0;
         uint32_t rank_base = 0;
+        // output row of this cell (recomputed here rather than kept live through the cuts)
+        size_t row = work;
+        long long self_id = (long long)work;
+        if (!P.query_xyz) {
+            self_id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + self_slot) + 3));
+            row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
+        }
+        const size_t srow = P.stage_by_work ? (size_t)work : row;
         if (!failed) {
 #pragma unroll
             for (int q = 0; q < MeshT::NWF; ++q) {

@@ -86,6 +86,25 @@ struct ClipParams {
     uint32_t flags;                // bit 0: serial walk only (TESS_FORCE_SERIAL=1, for A/B checks)
 };
 
+// radius / neighbour-cloud queries (query.cu)
+struct QueryParams {
+    const Particle* sorted;
+    const uint32_t* delim;
+    const uint64_t* groups_sorted;  // nullable
+    const ShellEntry* table;        // mode 2
+    uint32_t table_len, table_full;
+    GridSpec grid;
+    const double* xyz;              // n_query positions (device)
+    size_t n_query;
+    double radius;
+    int mode;                       // 0 cell radius, 1 real radius, 2 expand_all_in_radius
+    int64_t target_group;           // -1 = None
+    uint32_t* counts;               // pass 1
+    uint32_t* flags;
+    const uint64_t* offsets;        // pass 2
+    int64_t* indices;
+};
+
 #define TESS_CUDA_CHECK(expr)                                                                      \
     do {                                                                                           \
         cudaError_t e__ = (expr);                                                                  \
@@ -120,5 +139,6 @@ void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot
 void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s);
 void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s);
 double measure_fp64_peak_tflops();
+void launch_radius_query(const QueryParams& p, bool fill, cudaStream_t s);
 
 }  // namespace tess

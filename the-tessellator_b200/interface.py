@@ -159,6 +159,7 @@ class Diagram:
         self._n = 0
         self._box: Optional[np.ndarray] = None
         self._batches: dict = {}
+        self._host_pts: list = []  # (first index, array) of host-added particles, for Cell.compute_neighbor_cloud
 
     def close(self):
         if getattr(self, "_h", None):
@@ -195,6 +196,7 @@ class Diagram:
             a = np.ascontiguousarray(a)
         g = None if groups is None else np.ascontiguousarray(groups, dtype=np.uint64)
         check(_lib.lib().tess_diagram_add_particles(self._h, a.ctypes.data, a.shape[0], a.strides[0], None if g is None else g.ctypes.data, stream))
+        self._host_pts.append((self._n, a))
         self._n += a.shape[0]
 
     def add_particles_device(self, xyz_ptr: int, n: int, groups_ptr: int = 0, ids_ptr: int = 0, stream: int = 0) -> None:
@@ -203,9 +205,16 @@ class Diagram:
         check(_lib.lib().tess_diagram_add_particles_device(self._h, xyz_ptr, n, groups_ptr or None, ids_ptr or None, stream))
         self._n += n
 
+    def _position_of(self, index: int):
+        for lo, a in self._host_pts:
+            if lo <= index < lo + a.shape[0]:
+                return tuple(float(v) for v in a[index - lo, :3])
+        raise _lib.TessError(-5, "position of a particle added from device memory is not kept on the host")
+
     def _flush(self):
         if self._pending:
             pts = np.array(self._pending, dtype=np.float64)
+            self._host_pts.append((self._n, pts))
             grp = np.array(self._pending_groups, dtype=np.uint64)
             self._pending, self._pending_groups = [], []
             check(_lib.lib().tess_diagram_add_particles(self._h, pts.ctypes.data, pts.shape[0], 24, grp.ctypes.data, 0))
@@ -217,6 +226,7 @@ class Diagram:
         self._batches = {}
         check(_lib.lib().tess_diagram_clear(self._h))
         self._pending, self._pending_groups, self._n = [], [], 0
+        self._host_pts = []
         self.initialized = False
 
     def initialize(self, container: Optional[Polyhedron] = None, stream: int = 0) -> None:
@@ -299,6 +309,32 @@ class Diagram:
         check(_lib.lib().tess_compute_at_points(self._h, p.ctypes.data, p.shape[0], C.byref(o), C.byref(h)))
         return CellBatch(h.value, self.device)
 
+    # ---- radius queries (celery.rs:753-855) ---------------------------------------------------
+    def find_neighbors(self, points: np.ndarray, radius: float, mode: int, target_group: Optional[int] = None, stream: int = 0) -> list:
+        """Batch radius query: one list of particle ids per query point, in the reference's order."""
+        p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_find_neighbors(self._h, p.ctypes.data, p.shape[0], float(radius), mode, -1 if target_group is None else int(target_group), stream or None, C.byref(h)))
+        try:
+            po, pi = C.c_void_p(0), C.c_void_p(0)
+            check(_lib.lib().tess_query_offsets(h, C.byref(po)))
+            check(_lib.lib().tess_query_indices(h, C.byref(pi)))
+            m = p.shape[0]
+            off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(m + 1,)).astype(np.int64)
+            tot = int(off[-1])
+            idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int64)), shape=(tot,)).copy() if tot else np.zeros(0, np.int64)
+            return [idx[off[i]:off[i + 1]] for i in range(m)]
+        finally:
+            _lib.lib().tess_query_free(h)
+
+    def find_neighbors_in_cell_radius(self, x: float, y: float, z: float, radius: float) -> list:
+        """Celery::find_neighbors_in_cell_radius (celery.rs:802-819)."""
+        return self.find_neighbors(np.array([[x, y, z]]), radius, _lib.QUERY_CELL_RADIUS)[0].tolist()
+
+    def find_neighbors_in_real_radius(self, x: float, y: float, z: float, radius: float) -> list:
+        """Celery::find_neighbors_in_real_radius (celery.rs:825-855)."""
+        return self.find_neighbors(np.array([[x, y, z]]), radius, _lib.QUERY_REAL_RADIUS)[0].tolist()
+
     def _check_polyhedron(self, polyhedron: Polyhedron):
         if not np.array_equal(polyhedron.as_box(), self._box):
             raise _lib.TessError(-5, "the start polyhedron of a cell must be the diagram's container box")
@@ -363,6 +399,11 @@ class Cell:
         b = self._need()
         lo, hi = int(b.face_offsets[self._row]), int(b.face_offsets[self._row + 1])
         return [VoronoiFace(self, k) for k in range(lo, hi)]
+
+    def compute_neighbor_cloud(self, radius: float, target_group: Optional[int] = None) -> list:
+        """interface.rs:348-365: expand_all_in_radius(radius) around the cell's particle, filtered by group."""
+        pos = self.position if self.position is not None else self.diagram._position_of(self.index)
+        return self.diagram.find_neighbors(np.array([pos]), radius, _lib.QUERY_NEIGHBOR_CLOUD, target_group)[0].tolist()
 
     def original_index(self) -> Optional[int]:
         """interface.rs:387-389."""
