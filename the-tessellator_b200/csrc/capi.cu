@@ -614,7 +614,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     int64_t* st_nbr = tmp.get<int64_t>(n_rows * fstride);
     double* st_area = want_area ? tmp.get<double>(n_rows * fstride) : nullptr;
     double* st_vtx = want_vtx ? tmp.get<double>(n_rows * (size_t)vstride * 3) : nullptr;
-    uint32_t* ctrl = tmp.get<uint32_t>(8);  // [0] work counter, [1] n_failed, [2] n_failed (large pass)
+    uint32_t* ctrl = tmp.get<uint32_t>(16);  // [0] work counter, [1] n_failed, [2]/[3] n_failed of the redo passes, [5] table-only failures
     uint32_t* failed = tmp.get<uint32_t>(n_rows);
     double* query_dev = nullptr;
     if (query) {
@@ -622,7 +622,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         TESS_CUDA_CHECK(cudaMemcpyAsync(query_dev, query_host, sizeof(double) * 3 * n_query, cudaMemcpyHostToDevice, s));
     }
     void* scan_tmp = tmp.get<char>(scan_tmp_bytes(n_rows + 1));
-    TESS_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 8, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 16, s));
     tr.mark("allocations");
 
     const ShellTable& tab = d->table(R0, s);
@@ -667,29 +667,37 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
 
     // CSR offsets; one sync fetches {n_failed, total}
     launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
-    uint32_t n_failed = 0;
+    uint32_t n_failed = 0, n_table_only = 0;
     uint64_t total = 0;
     TESS_CUDA_CHECK(cudaMemcpyAsync(&n_failed, ctrl + 1, sizeof(n_failed), cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(&n_table_only, ctrl + 5, sizeof(n_table_only), cudaMemcpyDeviceToHost, s));
     TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
     tr.mark("clip + scan");
 
-    // ---- redo pass: cells the small tables / the default shell table could not finish ----------
-    uint32_t n_redo = 0;
-    int64_t* lg_nbr = nullptr;
-    double* lg_area = nullptr;
+    // ---- redo passes: cells the small tables / the default shell table could not finish -----------
+    //   A: the same small-cell kernel with a wider search table (cells in voids only ran out of table);
+    //   B: what still fails (more than 64 vertices / 40 faces) goes to the large-cell configuration,
+    //      with tables of doubled radius until every walk terminates.
+    uint32_t n_redo = 0, n_redo_b = 0;
+    int64_t *sa_nbr = nullptr, *lg_nbr = nullptr;
+    double *sa_area = nullptr, *lg_area = nullptr;
+    uint32_t* failed_b = nullptr;
     const uint32_t lstride = clip_large_fmax();
     if (n_failed > 0) {
-        if (n_failed > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
         n_redo = n_failed;
-        lg_nbr = tmp.get<int64_t>((size_t)n_redo * lstride);
-        lg_area = want_area ? tmp.get<double>((size_t)n_redo * lstride) : nullptr;
-        uint32_t* failed2 = tmp.get<uint32_t>(n_redo);
-        unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
-        int R = R0;
-        const int cpd_m1 = static_cast<int>(d->grid.cpd) - 1;
-        for (int attempt = 0; attempt < 12; ++attempt) {
-            R = std::min(std::max(2 * R, 16), std::max(cpd_m1, 1));
+        const int cpd_m1 = std::max(static_cast<int>(d->grid.cpd) - 1, 1);
+        int R = std::min(std::max(3 * R0, 24), cpd_m1);
+        const bool pass_a = n_table_only > 0;
+        if (!pass_a) {  // every failure is a table overflow of the small configuration: straight to pass B
+            failed_b = failed;
+            n_redo_b = n_redo;
+            n_redo = 0;
+        } else {
+        sa_nbr = tmp.get<int64_t>((size_t)n_redo * fstride);
+        sa_area = want_area ? tmp.get<double>((size_t)n_redo * fstride) : nullptr;
+        failed_b = tmp.get<uint32_t>(n_redo);
+        {
             const ShellTable& t2 = d->table(R, s);
             ClipParams Q = P;
             Q.table = t2.dev.as<ShellEntry>();
@@ -697,30 +705,59 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.table_full = t2.full ? 1u : 0u;
             Q.n_work = n_redo;
             Q.work_slots = failed;
-            Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.fstride = lstride; Q.stage_by_work = 1;
-            Q.st_vtx = nullptr;  // vertices of large cells are not staged (TESS_OUT_VERTICES covers small cells only)
-            Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
-            if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
-            Q.failed_slots = failed2;
+            Q.st_nbr = sa_nbr; Q.st_area = sa_area; Q.fstride = fstride; Q.stage_by_work = 1;
+            Q.st_vtx = nullptr;  // vertices of redone cells are not staged (TESS_OUT_VERTICES covers first-pass cells)
+            Q.failed_slots = failed_b;
             Q.n_failed = ctrl + 2;
             Q.failed_cap = n_redo;
             Q.mark_large = 1;
             TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 2, 0, sizeof(uint32_t), s));
-            launch_clip(Q, /*large=*/true, s);
-            uint32_t still = 0;
-            TESS_CUDA_CHECK(cudaMemcpyAsync(&still, ctrl + 2, sizeof(still), cudaMemcpyDeviceToHost, s));
+            launch_clip(Q, /*large=*/false, s);
+            TESS_CUDA_CHECK(cudaMemcpyAsync(&n_redo_b, ctrl + 2, sizeof(n_redo_b), cudaMemcpyDeviceToHost, s));
             TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-            if (still == 0 || t2.full) break;  // remaining failures (if any) are capacity overflows: reported in status
         }
-        if (want_cnt) {
-            unsigned long long h[CNT_N];
-            TESS_CUDA_CHECK(cudaMemcpyAsync(h, redo_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
-            TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-            for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] = h[i];
+        }
+        if (n_redo_b > 0) {
+            if (n_redo_b > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
+            lg_nbr = tmp.get<int64_t>((size_t)n_redo_b * lstride);
+            lg_area = want_area ? tmp.get<double>((size_t)n_redo_b * lstride) : nullptr;
+            uint32_t* failed_c = tmp.get<uint32_t>(n_redo_b);
+            unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
+            for (int attempt = 0; attempt < 12; ++attempt) {
+                const ShellTable& t2 = d->table(R, s);
+                ClipParams Q = P;
+                Q.table = t2.dev.as<ShellEntry>();
+                Q.table_len = t2.len;
+                Q.table_full = t2.full ? 1u : 0u;
+                Q.n_work = n_redo_b;
+                Q.work_slots = failed_b;
+                Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.fstride = lstride; Q.stage_by_work = 1;
+                Q.st_vtx = nullptr;
+                Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
+                if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
+                Q.failed_slots = failed_c;
+                Q.n_failed = ctrl + 3;
+                Q.failed_cap = n_redo_b;
+                Q.mark_large = 1;
+                TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 3, 0, sizeof(uint32_t), s));
+                launch_clip(Q, /*large=*/true, s);
+                uint32_t still = 0;
+                TESS_CUDA_CHECK(cudaMemcpyAsync(&still, ctrl + 3, sizeof(still), cudaMemcpyDeviceToHost, s));
+                TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+                if (still == 0 || t2.full) break;  // remaining failures (if any) are capacity overflows: reported in status
+                R = std::min(2 * R, cpd_m1);
+            }
+            if (want_cnt) {
+                unsigned long long h[CNT_N];
+                TESS_CUDA_CHECK(cudaMemcpyAsync(h, redo_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
+                TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+                for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] = h[i];
+            }
         }
         launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
         TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (std::getenv("TESS_TRACE")) std::fprintf(stderr, "[tess trace] redo: %u cells failed the first pass (%u for lack of table only); pass A re-ran %u, pass B (large cells, final R=%d) %u\n", n_failed, n_table_only, n_redo, R, n_redo_b);
     }
 
     tr.mark("redo");
@@ -729,8 +766,10 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     r->nbr = dmalloc<int64_t>(total, s);
     if (want_area) r->area = dmalloc<double>(total, s);
     launch_compact_faces(r->status, r->offsets, st_nbr, st_area, fstride, n_rows, r->nbr, r->area, s);
-    if (n_redo)
-        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lstride, n_redo, r->nbr, r->area, s);
+    if (n_redo)  // pass A rows (rows redone again by pass B are overwritten right after)
+        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, sa_nbr, sa_area, fstride, n_redo, r->nbr, r->area, s);
+    if (n_redo_b)
+        launch_compact_redo(failed_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lstride, n_redo_b, r->nbr, r->area, s);
     if (want_vtx) {
         launch_exclusive_scan_u32_to_u64(r->nverts, r->voffsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
         uint64_t tv = 0;
@@ -750,8 +789,9 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         cudaEventElapsedTime(&c, ev[2], ev[3]);
         cudaEventElapsedTime(&t, ev[0], ev[3]);
         r->ms_clip = a;
-        r->ms_redo = n_redo ? b : 0.0;  // includes the (small) scans before/after the redo pass
-        r->ms_outputs = c + (n_redo ? 0.0 : b);
+        const bool redone = n_redo || n_redo_b;
+        r->ms_redo = redone ? b : 0.0;  // includes the (small) scans before/after the redo passes
+        r->ms_outputs = c + (redone ? 0.0 : b);
         r->ms_total = t;
     }
     *out = r.release();

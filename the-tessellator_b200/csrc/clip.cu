@@ -160,7 +160,7 @@ struct WarpSmem {
     typename Cfg::Idx olist[32];             // outgoing half-edges of the cut, one per crossed face
     typename Cfg::Idx pred[32];              // crossing k -> the crossing that precedes it around the cut
     typename Cfg::Idx vfree[32];             // first free vertex slots
-    uint8_t kof[Cfg::REG ? Cfg::EMAX : 4];   // outgoing half-edge slot -> crossing index
+    uint8_t kof[Cfg::EMAX];                  // outgoing half-edge slot -> crossing index
     // candidate tile: bisector plane {n, offset} and id of the candidate each lane staged
     double4 cand_plane[32];
     long long cand_id[32];
@@ -189,7 +189,13 @@ struct Mesh {
     // and sits on the LIFO stack sm->estack[0, e_top) — the shape of pool.rs's Pool (free list +
     // append at the end) without a per-slot bitmask.
     int e_top, e_hwm;
+    // 32-slot words of the vertex / face tables that have ever been used (large cells sweep only these)
+    int v_words, f_words;
     int lane;
+    __device__ __forceinline__ int nwv() const { return Cfg::REG ? NWV : v_words; }
+    __device__ __forceinline__ int nwf() const { return Cfg::REG ? NWF : f_words; }
+    __device__ __forceinline__ void note_vertex(int slot) { if (!Cfg::REG && (slot >> 5) + 1 > v_words) v_words = (slot >> 5) + 1; }
+    __device__ __forceinline__ void note_face(int slot) { if (!Cfg::REG && (slot >> 5) + 1 > f_words) f_words = (slot >> 5) + 1; }
     static constexpr EW FREE_EDGE = ~(EW)0;
     static __device__ __forceinline__ bool e_is_free(EW w) { return e_face(w) == Cfg::NONE; }
     __device__ __forceinline__ int alloc_edge() {
@@ -228,6 +234,8 @@ struct Mesh {
         vlive.clear(); flive.clear();
         e_top = 0;
         e_hwm = 24;
+        v_words = 1;
+        f_words = 1;
         __syncwarp();
         if (lane < 8) {
             // FDL FDR FUR FUL BDL BDR BUR BUL (polyhedron.rs:288-295); corner + (-p)
@@ -257,6 +265,7 @@ struct Mesh {
         double m = 0.0;
 #pragma unroll
         for (int p = 0; p < NWV; ++p) {
+            if (p >= nwv()) break;
             const uint32_t lw = vlive.word(p);
             if (lw == 0u) continue;
             if ((lw >> lane) & 1u) {
@@ -306,7 +315,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
 
     // ---- 1. sweep the half-edge table ----------------------------------------------------------
     const int n_pass = M.edge_passes();
-    if (n_pass > 8) return CUT_FALLBACK;
+    if (n_pass > 32) return CUT_FALLBACK;  // deadbits holds one bit per pass
     uint32_t K = 0;
     uint32_t deadbits = 0;  // bit p: my half-edge of pass p dies
     uint32_t keep_lo = 0, keep_hi = 0;  // faces my surviving half-edges belong to (FMAX <= 64 here)
@@ -334,7 +343,11 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         K += __popc(om);
         deadbits |= (dead ? 1u : 0u) << p;
         if (keep) {
-            if (face < 32u) keep_lo |= 1u << face; else keep_hi |= 1u << (face - 32u);
+            if constexpr (Cfg::REG) {
+                if (face < 32u) keep_lo |= 1u << face; else keep_hi |= 1u << (face - 32u);
+            } else {
+                keep_lo = 1u;  // large cells: the face mask is rebuilt below, only if something died
+            }
         }
     }
     if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
@@ -397,17 +410,23 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     {
         int vfree_n = 0;
 #pragma unroll
-        for (int p = 0; p < MeshT::NWV; ++p) vfree_n += 32 - __popc(M.vlive.word(p));
+        vfree_n = 32 * (MeshT::NWV - M.nwv());
+        for (int p = 0; p < MeshT::NWV; ++p) {
+            if (p >= M.nwv()) break;
+            vfree_n += 32 - __popc(M.vlive.word(p));
+        }
         const int efree_n = M.e_top + (Cfg::E_LIMIT - M.e_hwm);
         if ((int)K > vfree_n || 2 * (int)K > efree_n) return -1;
     }
     const int cap_face = M.flive.alloc(Cfg::FMAX);
     if (cap_face < 0) return -1;
+    M.note_face(cap_face);
     // first free vertex slots, in ascending order (what repeated lowest-free-bit allocation yields)
     {
         uint32_t base = 0;
 #pragma unroll
         for (int p = 0; p < MeshT::NWV; ++p) {
+            if (base >= 32u) break;
             const uint32_t fr = ~M.vlive.word(p);
             if ((fr >> lane) & 1u) {
                 const uint32_t rk = base + __popc(fr & lt);
@@ -443,7 +462,9 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         sm->edge[ck] = MeshT::pack(ck_pred, br, nv_pred, (uint32_t)cap_face);  // cap edge (:592-598 / D6)
         sm->edge[o] = MeshT::pack(br, fo, nv_pred, f);                // :550 + :590
         sm->fstart[f] = (Idx)o;                                       // :578-580
-        if (nv < 32u) nb_lo = 1u << nv; else nb_hi = 1u << (nv - 32u);
+        if constexpr (Cfg::REG) {
+            if (nv < 32u) nb_lo = 1u << nv; else nb_hi = 1u << (nv - 32u);
+        }
     }
     if (lane == 0) {
         sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (:479-482)
@@ -458,10 +479,18 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     }
     __syncwarp();
     // ---- retire: Outside vertices, dead half-edges (ascending slot order), faces without edges ----
-    nb_lo = __reduce_or_sync(FULL, nb_lo);
-    nb_hi = __reduce_or_sync(FULL, nb_hi);
-    M.vlive.set_word(0, (M.vlive.word(0) & ~M.outside.word(0)) | nb_lo);
-    if (MeshT::NWV > 1) M.vlive.set_word(1, (M.vlive.word(1) & ~M.outside.word(1)) | nb_hi);
+    if constexpr (Cfg::REG) {
+        nb_lo = __reduce_or_sync(FULL, nb_lo);
+        nb_hi = __reduce_or_sync(FULL, nb_hi);
+        M.vlive.set_word(0, (M.vlive.word(0) & ~M.outside.word(0)) | nb_lo);
+        if (MeshT::NWV > 1) M.vlive.set_word(1, (M.vlive.word(1) & ~M.outside.word(1)) | nb_hi);
+    } else {
+        for (int p = lane; p < M.nwv(); p += 32) sm->m_vlive[p] &= ~sm->m_outside[p];
+        __syncwarp();
+        if (act) atomicOr(&sm->m_vlive[nv >> 5], 1u << (nv & 31u));
+        M.note_vertex((int)__reduce_max_sync(FULL, act ? nv : 0u));
+        __syncwarp();
+    }
     if (__any_sync(FULL, deadbits != 0u)) {
         const int old_top = M.e_top;
         for (int p = 0; p < n_pass; ++p) {
@@ -473,10 +502,27 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         __syncwarp();
         for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
         // a face can only lose all its half-edges when some half-edge died
-        keep_lo = __reduce_or_sync(FULL, keep_lo);
-        keep_hi = __reduce_or_sync(FULL, keep_hi);
-        M.flive.set_word(0, M.flive.word(0) & keep_lo);
-        if (MeshT::NWF > 1) M.flive.set_word(1, M.flive.word(1) & keep_hi);
+        if constexpr (Cfg::REG) {
+            keep_lo = __reduce_or_sync(FULL, keep_lo);
+            keep_hi = __reduce_or_sync(FULL, keep_hi);
+            M.flive.set_word(0, M.flive.word(0) & keep_lo);
+            if (MeshT::NWF > 1) M.flive.set_word(1, M.flive.word(1) & keep_hi);
+        } else {
+            // faces that still own a half-edge: one more sweep (the retired slots are marked free by now)
+            for (int q = lane; q < M.nwf(); q += 32) sm->m_fkeep[q] = 0u;
+            __syncwarp();
+            const int np2 = M.edge_passes();
+            for (int p = 0; p < np2; ++p) {
+                const EW w = M.edge_of_pass(p);
+                if (!MeshT::e_is_free(w)) {
+                    const uint32_t face = MeshT::e_face(w);
+                    atomicOr(&sm->m_fkeep[face >> 5], 1u << (face & 31u));
+                }
+            }
+            __syncwarp();
+            for (int q = lane; q < M.nwf(); q += 32) sm->m_flive[q] &= sm->m_fkeep[q];
+            __syncwarp();
+        }
     }
     M.flive.set((uint32_t)cap_face);
     cnt_nv += K;
@@ -501,6 +547,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     uint32_t nlive = 0;
 #pragma unroll
     for (int p = 0; p < MeshT::NWV; ++p) {
+        if (p >= M.nwv()) break;
         const uint32_t lw = M.vlive.word(p);
         M.vbefore.set_word(p, lw);
         if (lw == 0u) {  // an empty word of slots (the upper half of a small cell, most of the time)
@@ -524,11 +571,9 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     if (!any_out) return 0;  // polyhedron.rs:408-410
 
     // ---- fast path: no vertex on the plane -> the whole cut in lane-parallel form ----------------
-    if constexpr (Cfg::REG) {
-        if (!any_incident && !serial_only) {
-            const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv);
-            if (rc != CUT_FALLBACK) return rc;
-        }
+    if (!any_incident && !serial_only) {
+        const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv);
+        if (rc != CUT_FALLBACK) return rc;
     }
 
     // ---- first edge (slot order) with target Inside whose flip's target is Outside; the walk
@@ -555,6 +600,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     const int cap_first = M.alloc_edge();
     const int cap_face = M.flive.alloc(Cfg::FMAX);
     if (cap_first < 0 || cap_face < 0) return -1;
+    M.note_face(cap_face);
     sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (polyhedron.rs:479-482)
     sm->fstart[cap_face] = (typename Cfg::Idx)cap_first;
     sm->edge[cap_first] = MeshT::pack(Cfg::NONE, Cfg::NONE, Cfg::NONE, (uint32_t)cap_face);
@@ -611,6 +657,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             const int nv = M.vlive.alloc(Cfg::VMAX);
             const int br = M.alloc_edge();
             if (nv < 0 || br < 0) return -1;
+            M.note_vertex(nv);
             sm->xlist[nbridge & 31u] = MeshT::pack(pv, cv, (uint32_t)nv, M.outside.test(pv) ? 0u : 1u);
             const uint32_t f = MeshT::e_face(w_out);
             sm->fstart[f] = (typename Cfg::Idx)out_e;  // :578-580
@@ -655,7 +702,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     //      through non-Inside vertices; half-edges with both ends removed; faces left without edges.
     uint32_t missing = 0;
 #pragma unroll
-    for (int p = 0; p < MeshT::NWV; ++p) missing |= (M.vbefore.word(p) & ~M.inside.word(p) & ~M.removed.word(p));
+    for (int p = 0; p < MeshT::NWV; ++p) {
+        if (p >= M.nwv()) break;
+        missing |= (M.vbefore.word(p) & ~M.inside.word(p) & ~M.removed.word(p));
+    }
     if (missing) {
         // interior of the cut-off region: grow `removed` along edges between non-Inside vertices
         bool changed = true;
@@ -687,7 +737,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         }
     }
 #pragma unroll
-    for (int p = 0; p < MeshT::NWV; ++p) M.vlive.set_word(p, M.vlive.word(p) & ~M.removed.word(p));
+    for (int p = 0; p < MeshT::NWV; ++p) {
+        if (p >= M.nwv()) break;
+        M.vlive.set_word(p, M.vlive.word(p) & ~M.removed.word(p));
+    }
 
     M.fkeep.clear();
     if constexpr (!Cfg::REG) __syncwarp();
@@ -729,7 +782,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
     if (__any_sync(FULL, inconsistent)) status |= ST_INCONSISTENT;
 #pragma unroll
-    for (int q = 0; q < MeshT::NWF; ++q) M.flive.set_word(q, M.flive.word(q) & M.fkeep.word(q));
+    for (int q = 0; q < MeshT::NWF; ++q) {
+        if (q >= M.nwf()) break;
+        M.flive.set_word(q, M.flive.word(q) & M.fkeep.word(q));
+    }
     __syncwarp();
     return 1;
 }
@@ -919,7 +975,10 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         // ---- results: weighted normals, areas, volume, neighbours ------------------------------
         uint32_t nf = 0;
 #pragma unroll
-        for (int q = 0; q < MeshT::NWF; ++q) nf += __popc(M.flive.word(q));
+        for (int q = 0; q < MeshT::NWF; ++q) {
+            if (q >= M.nwf()) break;
+            nf += __popc(M.flive.word(q));
+        }
         double vol_part = 0.0;
         uint32_t rank_base = 0;
         // output row of this cell (recomputed here rather than kept live through the cuts)
@@ -933,6 +992,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         if (!failed) {
 #pragma unroll
             for (int q = 0; q < MeshT::NWF; ++q) {
+                if (q >= M.nwf()) break;
                 const uint32_t lw = M.flive.word(q);
                 if (lw == 0u) continue;
                 if ((lw >> lane) & 1u) {
@@ -976,6 +1036,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
             uint32_t vb = 0;
 #pragma unroll
             for (int p = 0; p < MeshT::NWV; ++p) {
+                if (p >= M.nwv()) break;
                 const uint32_t lw = M.vlive.word(p);
                 if ((lw >> lane) & 1u) {
                     const uint32_t r = vb + __popc(lw & ((1u << lane) - 1u));
@@ -995,6 +1056,8 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
             if (bad && P.failed_slots && !P.query_xyz) {
                 const uint32_t k = atomicAdd(P.n_failed, 1u);
                 if (k < P.failed_cap) P.failed_slots[k] = self_slot;
+                // cells that only ran out of search table (a wider table in the same configuration will do)
+                if ((status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) == 0) atomicAdd(P.n_failed + 4, 1u);
             }
             const bool empty = (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) != 0;
             P.vol[row] = empty ? 0.0 : __ddiv_rn(vol_part, 6.0);

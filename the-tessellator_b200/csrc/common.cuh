@@ -80,7 +80,7 @@ struct ClipParams {
     uint32_t* work_counter;        // dynamic work distribution
     // cells this configuration could not finish (capacity / table exhausted): slots appended here
     uint32_t* failed_slots;        // nullable
-    uint32_t* n_failed;
+    uint32_t* n_failed;            // [0] count of failed cells; [4] those that only exhausted the search table
     uint32_t failed_cap;
     uint32_t mark_large;           // OR ST_LARGE_PATH into the status of every row written
     uint32_t flags;                // bit 0: serial walk only (TESS_FORCE_SERIAL=1, for A/B checks)

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) compact_redo_kernel(const uint32_t* __res
     if (w >= n_work) return;
     const uint32_t slot = work_slots[w];
     const size_t row = row_of_slot ? row_of_slot[slot] : (size_t)(slot - row_base);
-    const uint32_t nf = nfaces[row];
+    const uint32_t nf = min(nfaces[row], fstride);  // a row redone later by a larger configuration may exceed this stage's stride
     const uint64_t o = offsets[row];
     for (uint32_t k = lane; k < nf; k += 32) {
         nbr[o + k] = st_nbr[w * fstride + k];
