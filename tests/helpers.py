@@ -52,6 +52,18 @@ def sorted_cells(offsets: np.ndarray, neighbors: np.ndarray, areas: np.ndarray |
     return neighbors[order], (None if areas is None else areas[order])
 
 
+def assert_cells_identical(got, ref, what=""):
+    """Bit-for-bit: same faces in the same (face-slot) order, same volumes, same areas.  The CUDA path
+    allocates half-edge and face slots in pool.rs's LIFO order and sums in the reference's order, so it
+    reproduces the oracle exactly, not just within the 1e-12 bar."""
+    assert np.array_equal(np.asarray(got.face_offsets, np.int64), np.asarray(ref.face_offsets, np.int64)), f"{what}: face counts differ"
+    assert np.array_equal(np.asarray(got.neighbors, np.int64), np.asarray(ref.neighbors, np.int64)), f"{what}: neighbour lists differ (order included)"
+    gv, rv = np.asarray(got.volumes), np.asarray(ref.volumes)
+    assert np.array_equal(gv, rv), f"{what}: {int((gv != rv).sum())} volumes differ bitwise, max rel {np.max(np.abs(gv - rv) / np.abs(rv)):.3e}"
+    ga, ra = np.asarray(got.areas), np.asarray(ref.areas)
+    assert np.array_equal(ga, ra), f"{what}: {int((ga != ra).sum())} areas differ bitwise"
+
+
 def assert_cells_match(got, ref, area_rtol=AREA_RTOL, vol_rtol=VOL_RTOL, what=""):
     """got / ref expose volumes, face_offsets, neighbors, areas (CellBatch or oracle CellResults).
     Topology: the sorted neighbour lists must be identical.  Volumes / areas: relative tolerance."""

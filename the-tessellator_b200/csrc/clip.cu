@@ -155,6 +155,7 @@ struct WarpSmem {
     typename Cfg::EdgeWord edge[Cfg::EMAX];  // {next, flip, target, face}
     typename Cfg::Idx fstart[Cfg::FMAX];
     typename Cfg::Idx estack[Cfg::EMAX];     // free half-edge slots (LIFO, like pool.rs's free list)
+    typename Cfg::Idx fstack[Cfg::FMAX];     // free face slots (LIFO)
     typename Cfg::EdgeWord xlist[32];        // crossings of the current cut: {outside end, inside end, new vertex, copy flag}
     // scratch of the warp-parallel cut (small configuration only)
     typename Cfg::Idx olist[32];             // outgoing half-edges of the cut, one per crossed face
@@ -189,6 +190,7 @@ struct Mesh {
     // and sits on the LIFO stack sm->estack[0, e_top) — the shape of pool.rs's Pool (free list +
     // append at the end) without a per-slot bitmask.
     int e_top, e_hwm;
+    int f_top, f_hwm;  // same for faces: sm->fstack[0, f_top) + high-water mark (flive stays the iteration mask)
     // 32-slot words of the vertex / face tables that have ever been used (large cells sweep only these)
     int v_words, f_words;
     int lane;
@@ -202,6 +204,23 @@ struct Mesh {
         if (e_top > 0) return (int)sm->estack[--e_top];
         if (e_hwm < Cfg::E_LIMIT) return e_hwm++;
         return -1;
+    }
+    // Pool::add for faces (pool.rs:85-110): most recently freed slot first, else append
+    __device__ __forceinline__ int alloc_face() {
+        int slot;
+        if (f_top > 0) slot = (int)sm->fstack[--f_top];
+        else if (f_hwm < Cfg::FMAX) slot = f_hwm++;
+        else return -1;
+        flive.set((uint32_t)slot);
+        note_face(slot);
+        return slot;
+    }
+    // Pool::remove for every face of word q that lost all its half-edges, in ascending slot order
+    __device__ __forceinline__ void retire_faces(int q, uint32_t dead_word) {
+        if (dead_word == 0u) return;
+        if ((dead_word >> lane) & 1u) sm->fstack[f_top + __popc(dead_word & ((1u << lane) - 1u))] = (Idx)(32 * q + lane);
+        f_top += __popc(dead_word);
+        __syncwarp();
     }
     // edge word of slot 32*p+lane, FREE_EDGE beyond the high-water mark
     __device__ __forceinline__ EW edge_of_pass(int p) const {
@@ -234,6 +253,8 @@ struct Mesh {
         vlive.clear(); flive.clear();
         e_top = 0;
         e_hwm = 24;
+        f_top = 0;
+        f_hwm = 6;
         v_words = 1;
         f_words = 1;
         __syncwarp();
@@ -416,11 +437,10 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
             vfree_n += 32 - __popc(M.vlive.word(p));
         }
         const int efree_n = M.e_top + (Cfg::E_LIMIT - M.e_hwm);
-        if ((int)K > vfree_n || 2 * (int)K > efree_n) return -1;
+        if ((int)K > vfree_n || 2 * (int)K + 1 > efree_n) return -1;
     }
-    const int cap_face = M.flive.alloc(Cfg::FMAX);
+    const int cap_face = M.alloc_face();
     if (cap_face < 0) return -1;
-    M.note_face(cap_face);
     // first free vertex slots, in ascending order (what repeated lowest-free-bit allocation yields)
     {
         uint32_t base = 0;
@@ -437,14 +457,15 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     }
     __syncwarp();
     // ---- 4. new vertex, bridge and cap half-edge of every crossing ------------------------------
-    // slots are handed out exactly as the serial walk would: it pops cap_first, then per crossing
-    // a bridge and (from the second crossing on) a cap half-edge; vertices by lowest free slot.
+    // Half-edge slots are handed out in the order of the reference's walk (Pool::add, pool.rs:85-110):
+    // cap_first (:478), then per crossing the bridge (:582) and the NEXT crossing's cap edge (:592);
+    // the cap edge created by the last crossing is redundant and goes straight back.
     auto pop_slot = [&](int j) -> uint32_t { return j < M.e_top ? (uint32_t)sm->estack[M.e_top - 1 - j] : (uint32_t)(M.e_hwm + (j - M.e_top)); };
     uint32_t nv = 0, ck = 0, br = 0;
     if (act) {
         nv = sm->vfree[wi];
-        ck = pop_slot(wi == 0u ? 0 : 2 * (int)wi + 1);
-        br = pop_slot(wi == 0u ? 1 : 2 * (int)wi);
+        ck = pop_slot(2 * (int)wi);
+        br = pop_slot(2 * (int)wi + 1);
     }
     const uint32_t pk = act ? (uint32_t)sm->pred[lane] : 0u;
     const uint32_t nv_pred = __shfl_sync(FULL, nv, (int)pk);  // previous_intersection (:550, :600)
@@ -470,12 +491,19 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (:479-482)
         sm->fstart[cap_face] = (Idx)ck0;
     }
-    // allocator state after 2K pops
+    // allocator state after 2K+1 pops; the redundant cap edge is freed first (it lands where it was
+    // when it came off the stack)
     {
-        const int pops = 2 * (int)K;
+        const uint32_t red = pop_slot(2 * (int)K);
+        const int pops = 2 * (int)K + 1;
         const int from_stack = pops < M.e_top ? pops : M.e_top;
         M.e_hwm += pops - from_stack;
         M.e_top -= from_stack;
+        if (lane == 0) {
+            sm->estack[M.e_top] = (Idx)red;
+            sm->edge[red] = MeshT::FREE_EDGE;
+        }
+        M.e_top += 1;
     }
     __syncwarp();
     // ---- retire: Outside vertices, dead half-edges (ascending slot order), faces without edges ----
@@ -503,10 +531,15 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         for (int i = old_top + lane; i < M.e_top; i += 32) sm->edge[sm->estack[i]] = MeshT::FREE_EDGE;
         // a face can only lose all its half-edges when some half-edge died
         if constexpr (Cfg::REG) {
-            keep_lo = __reduce_or_sync(FULL, keep_lo);
-            keep_hi = __reduce_or_sync(FULL, keep_hi);
-            M.flive.set_word(0, M.flive.word(0) & keep_lo);
-            if (MeshT::NWF > 1) M.flive.set_word(1, M.flive.word(1) & keep_hi);
+            keep_lo = __reduce_or_sync(FULL, keep_lo) | (cap_face < 32 ? 1u << cap_face : 0u);
+            keep_hi = __reduce_or_sync(FULL, keep_hi) | (cap_face >= 32 ? 1u << (cap_face - 32) : 0u);
+            const uint32_t o0 = M.flive.word(0), o1 = MeshT::NWF > 1 ? M.flive.word(1) : 0u;
+            M.flive.set_word(0, o0 & keep_lo);
+            M.retire_faces(0, o0 & ~keep_lo);
+            if (MeshT::NWF > 1) {
+                M.flive.set_word(1, o1 & keep_hi);
+                M.retire_faces(1, o1 & ~keep_hi);
+            }
         } else {
             // faces that still own a half-edge: one more sweep (the retired slots are marked free by now)
             for (int q = lane; q < M.nwf(); q += 32) sm->m_fkeep[q] = 0u;
@@ -520,11 +553,15 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
                 }
             }
             __syncwarp();
-            for (int q = lane; q < M.nwf(); q += 32) sm->m_flive[q] &= sm->m_fkeep[q];
+            for (int q = 0; q < M.nwf(); ++q) {
+                const uint32_t o = sm->m_flive[q], k = sm->m_fkeep[q];
+                __syncwarp();
+                if (lane == 0) sm->m_flive[q] = o & k;
+                M.retire_faces(q, o & ~k);
+            }
             __syncwarp();
         }
     }
-    M.flive.set((uint32_t)cap_face);
     cnt_nv += K;
     __syncwarp();
     return 1;
@@ -598,9 +635,8 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 
     // ---- the walk (polyhedron.rs:475-623), warp-uniform ---------------------------------------
     const int cap_first = M.alloc_edge();
-    const int cap_face = M.flive.alloc(Cfg::FMAX);
+    const int cap_face = M.alloc_face();
     if (cap_first < 0 || cap_face < 0) return -1;
-    M.note_face(cap_face);
     sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (polyhedron.rs:479-482)
     sm->fstart[cap_face] = (typename Cfg::Idx)cap_first;
     sm->edge[cap_first] = MeshT::pack(Cfg::NONE, Cfg::NONE, Cfg::NONE, (uint32_t)cap_face);
@@ -608,7 +644,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     M.removed.clear();  // vertices_to_destroy (polyhedron.rs:487)
     uint32_t out_e = (uint32_t)first;
     uint32_t prev_int = Cfg::NONE;  // previous_intersection
-    uint32_t cap_prev = (uint32_t)cap_first;
+    uint32_t cap_cur = (uint32_t)cap_first;  // outside_face_edge_index (:483)
     uint32_t nbridge = 0;
     int budget = 2 * Cfg::EMAX;  // a consistent mesh cannot need more steps
 
@@ -661,21 +697,15 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             sm->xlist[nbridge & 31u] = MeshT::pack(pv, cv, (uint32_t)nv, M.outside.test(pv) ? 0u : 1u);
             const uint32_t f = MeshT::e_face(w_out);
             sm->fstart[f] = (typename Cfg::Idx)out_e;  // :578-580
-            uint32_t capk;
-            if (nbridge == 0) {
-                capk = (uint32_t)cap_first;
-                M.set_field((uint32_t)cap_first, 1, (uint32_t)br);  // :589
-            } else {
-                // the cap edge paired with this bridge: the reference creates it at the end of the
-                // previous crossing (:592-598) with target = previous intersection
-                const int ce = M.alloc_edge();
-                if (ce < 0) return -1;
-                capk = (uint32_t)ce;
-                sm->edge[capk] = MeshT::pack(cap_prev, (uint32_t)br, prev_int, (uint32_t)cap_face);
-            }
-            sm->edge[br] = MeshT::pack(cur_e, capk, (uint32_t)nv, f);                     // :582-587
+            // bridge (:582-587), paired with the current cap edge (:589); then, as the reference does,
+            // the cap edge of the NEXT crossing (:592-598): target = this intersection, next = current cap edge
+            sm->edge[br] = MeshT::pack(cur_e, cap_cur, (uint32_t)nv, f);
+            M.set_field(cap_cur, 1, (uint32_t)br);
             sm->edge[out_e] = MeshT::pack((uint32_t)br, MeshT::e_flip(w_out), prev_int, f);  // :550 + :590
-            cap_prev = capk;
+            const int nc = M.alloc_edge();
+            if (nc < 0) return -1;
+            sm->edge[nc] = MeshT::pack(cap_cur, Cfg::NONE, (uint32_t)nv, (uint32_t)cap_face);
+            cap_cur = (uint32_t)nc;
             prev_int = (uint32_t)nv;
             ++nbridge;
             if ((nbridge & 31u) == 0u) emit_vertices(32u);
@@ -691,10 +721,18 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     if (nbridge & 31u) emit_vertices(nbridge & 31u);
     cnt_nv += nbridge;
 
-    // close the loop: first outgoing edge and first cap edge end at the last intersection
-    M.set_field((uint32_t)first, 2, prev_int);
-    M.set_field((uint32_t)cap_first, 2, prev_int);
-    M.set_field((uint32_t)cap_first, 0, cap_prev);
+    // close the loop: first outgoing edge and first cap edge end at the last intersection;
+    // the cap edge created by the last crossing is the redundant twin of cap_first and is freed first
+    {
+        const uint32_t redundant = cap_cur;
+        const uint32_t last_paired = MeshT::e_next(sm->edge[redundant]);
+        M.set_field((uint32_t)first, 2, prev_int);
+        M.set_field((uint32_t)cap_first, 2, prev_int);
+        M.set_field((uint32_t)cap_first, 0, last_paired);
+        sm->edge[redundant] = MeshT::FREE_EDGE;
+        sm->estack[M.e_top] = (typename Cfg::Idx)redundant;
+        M.e_top += 1;
+    }
     __syncwarp();
 
     // ---- retire what was cut off (clean_up_vertices / clean_up_edges / mark_sweep,
@@ -784,7 +822,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 #pragma unroll
     for (int q = 0; q < MeshT::NWF; ++q) {
         if (q >= M.nwf()) break;
-        M.flive.set_word(q, M.flive.word(q) & M.fkeep.word(q));
+        const uint32_t o = M.flive.word(q), k = M.fkeep.word(q);
+        if constexpr (!Cfg::REG) __syncwarp();
+        M.flive.set_word(q, o & k);
+        M.retire_faces(q, o & ~k);
     }
     __syncwarp();
     return 1;
@@ -995,6 +1036,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 if (q >= M.nwf()) break;
                 const uint32_t lw = M.flive.word(q);
                 if (lw == 0u) continue;
+                double contrib = 0.0;
                 if ((lw >> lane) & 1u) {
                     const int f = 32 * q + lane;
                     // Polyhedron::weighted_normal (polyhedron.rs:776-808)
@@ -1018,7 +1060,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                         e = MeshT::e_next(w);
                     }
                     const double area = mul(0.5, __dsqrt_rn(dot(wn, wn)));  // interface.rs:408-410
-                    vol_part = addd(vol_part, dot(A, wn));                   // polyhedron.rs:849
+                    contrib = dot(A, wn);                                    // polyhedron.rs:849
                     const uint32_t rank = rank_base + __popc(lw & ((1u << lane) - 1u));
                     if (rank < P.fstride) {
                         P.st_nbr[srow * P.fstride + rank] = sm->fnbr[f];
@@ -1026,12 +1068,13 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     }
                 }
                 rank_base += __popc(lw);
+                // volume = volume + dot(...) face after face in ascending slot order (polyhedron.rs:843-850):
+                // the same summation order as the reference, so the sum is reproduced bit for bit
+                for (uint32_t m = lw; m; m &= m - 1u) vol_part = addd(vol_part, __shfl_sync(FULL, contrib, __ffs(m) - 1));
             }
             if (nf > P.fstride) status |= ST_CAPACITY_OVERFLOW;
         }
         // volume = (sum over faces) / 6 (polyhedron.rs:854)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vol_part = addd(vol_part, __shfl_xor_sync(FULL, vol_part, o));
         if (P.st_vtx && !failed) {
             uint32_t vb = 0;
 #pragma unroll
