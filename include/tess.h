@@ -152,6 +152,11 @@ int tess_result_status(tess_result* r, const uint32_t** out);        /* n_cells,
 int tess_result_cell_ids(tess_result* r, const int64_t** out);       /* n_cells */
 int tess_result_vertex_offsets(tess_result* r, const uint64_t** out); /* n_cells+1 (TESS_OUT_VERTICES) */
 int tess_result_vertices(tess_result* r, const double** out);         /* xyz triples, cell-local coordinates */
+/* VoronoiFace::compute_vertices (interface.rs:403-405 -> Polyhedron::compute_face_vertices, polyhedron.rs:897-919):
+ * for face k (same numbering as neighbours/areas) the loop entries face_vertex_offsets[k] .. [k+1] are indices into
+ * the OWNING CELL's vertex list (add vertex_offsets[cell]); order = from the face's starting edge, following next. */
+int tess_result_face_vertex_offsets(tess_result* r, const uint64_t** out); /* n_faces+1 (TESS_OUT_VERTICES) */
+int tess_result_face_vertex_indices(tess_result* r, const uint32_t** out);
 /* counters[8] = candidates visited, candidates tested, vertex classifications, cuts,
  * new vertices, table entries consumed, degenerate skips, faces */
 int tess_result_counters(tess_result* r, uint64_t counters[8]);

@@ -58,6 +58,10 @@ class CellBatch {
         check(tess_result_neighbors(r_, &neighbors));
         check(tess_result_areas(r_, &areas));
         check(tess_result_status(r_, &status));
+        // geometry is present only when TESS_OUT_VERTICES was requested
+        if (tess_result_vertex_offsets(r_, &vertex_offsets) != TESS_OK || tess_result_vertices(r_, &vertices) != TESS_OK ||
+            tess_result_face_vertex_offsets(r_, &face_vertex_offsets) != TESS_OK || tess_result_face_vertex_indices(r_, &face_vertex_indices) != TESS_OK)
+            vertex_offsets = nullptr;
     }
     ~CellBatch() { tess_result_free(r_); }
     CellBatch(const CellBatch&) = delete;
@@ -68,6 +72,10 @@ class CellBatch {
     const int64_t* neighbors = nullptr;
     const double* areas = nullptr;
     const uint32_t* status = nullptr;
+    const uint64_t* vertex_offsets = nullptr;       // n_cells+1, or nullptr without TESS_OUT_VERTICES
+    const double* vertices = nullptr;               // xyz triples, cell-local coordinates
+    const uint64_t* face_vertex_offsets = nullptr;  // n_faces+1
+    const uint32_t* face_vertex_indices = nullptr;  // ranks in the owning cell's vertex list
     tess_result* handle() const { return r_; }
 
    private:
@@ -125,9 +133,11 @@ class Diagram {
     Cell get_cell_at_particle(const Vector3& point, const Polyhedron& polyhedron, std::optional<double> search_radius = std::nullopt, std::optional<size_t> target_group = std::nullopt);
 
     /// explicit batch fast path (extension): every cell in one call
-    std::shared_ptr<CellBatch> compute_all_cells(std::optional<double> search_radius = std::nullopt, std::optional<size_t> target_group = std::nullopt) {
+    std::shared_ptr<CellBatch> compute_all_cells(std::optional<double> search_radius = std::nullopt, std::optional<size_t> target_group = std::nullopt,
+                                                 bool with_vertices = false) {
         tess_opts o;
         tess_opts_default(&o);
+        if (with_vertices) o.outputs |= TESS_OUT_VERTICES;
         if (search_radius) o.search_radius = *search_radius;
         if (target_group) o.target_group = static_cast<int64_t>(*target_group);
         tess_result* r = nullptr;
@@ -137,6 +147,7 @@ class Diagram {
     std::shared_ptr<CellBatch> compute_cells_at(const Vector3* pts, size_t m, std::optional<double> search_radius, std::optional<size_t> target_group) {
         tess_opts o;
         tess_opts_default(&o);
+        o.outputs |= TESS_OUT_VERTICES;
         if (search_radius) o.search_radius = *search_radius;
         if (target_group) o.target_group = static_cast<int64_t>(*target_group);
         tess_result* r = nullptr;
@@ -162,7 +173,7 @@ class Diagram {
         const auto key = std::make_pair(radius ? *radius : std::numeric_limits<double>::quiet_NaN(), group ? static_cast<int64_t>(*group) : int64_t(-1));
         for (auto& kv : batches_)
             if ((kv.first.first == key.first || (std::isnan(kv.first.first) && std::isnan(key.first))) && kv.first.second == key.second) return kv.second;
-        auto b = compute_all_cells(radius, group);
+        auto b = compute_all_cells(radius, group, /*with_vertices=*/true);
         batches_.push_back({key, b});
         return b;
     }
@@ -195,6 +206,13 @@ class Cell {
         const CellBatch& b = need();
         return std::vector<int64_t>(b.neighbors + b.face_offsets[row_], b.neighbors + b.face_offsets[row_ + 1]);
     }
+    std::vector<Vector3> compute_vertices() {                 // interface.rs:368-370 (cell-local coordinates)
+        const CellBatch& b = need();
+        std::vector<Vector3> out;
+        if (!b.vertex_offsets) throw Error(TESS_ERR_STATE, "vertices were not computed");
+        for (uint64_t v = b.vertex_offsets[row_]; v < b.vertex_offsets[row_ + 1]; ++v) out.push_back(Vector3{b.vertices[3 * v], b.vertices[3 * v + 1], b.vertices[3 * v + 2]});
+        return out;
+    }
     std::vector<VoronoiFace> compute_faces();                 // interface.rs:373-384
     std::optional<size_t> original_index() const { return index_; }  // interface.rs:387-389
     uint32_t status() { return need().status[row_]; }
@@ -222,18 +240,29 @@ class VoronoiFace {
    public:
     double compute_area() const { return batch_->areas[k_]; }          // interface.rs:408-410
     int64_t compute_neighbor() const { return batch_->neighbors[k_]; }  // interface.rs:413-416
+    std::vector<Vector3> compute_vertices() const {                       // interface.rs:403-405: loop order
+        const CellBatch& b = *batch_;
+        if (!b.vertex_offsets) throw Error(TESS_ERR_STATE, "vertices were not computed");
+        std::vector<Vector3> out;
+        const uint64_t base = b.vertex_offsets[row_];
+        for (uint64_t i = b.face_vertex_offsets[k_]; i < b.face_vertex_offsets[k_ + 1]; ++i) {
+            const uint64_t v = base + b.face_vertex_indices[i];
+            out.push_back(Vector3{b.vertices[3 * v], b.vertices[3 * v + 1], b.vertices[3 * v + 2]});
+        }
+        return out;
+    }
 
    private:
     friend class Cell;
-    VoronoiFace(std::shared_ptr<CellBatch> b, uint64_t k) : batch_(std::move(b)), k_(k) {}
+    VoronoiFace(std::shared_ptr<CellBatch> b, uint64_t k, uint64_t row) : batch_(std::move(b)), k_(k), row_(row) {}
     std::shared_ptr<CellBatch> batch_;
-    uint64_t k_;
+    uint64_t k_, row_;
 };
 
 inline std::vector<VoronoiFace> Cell::compute_faces() {
     const CellBatch& b = need();
     std::vector<VoronoiFace> out;
-    for (uint64_t k = b.face_offsets[row_]; k < b.face_offsets[row_ + 1]; ++k) out.push_back(VoronoiFace(batch_, k));
+    for (uint64_t k = b.face_offsets[row_]; k < b.face_offsets[row_ + 1]; ++k) out.push_back(VoronoiFace(batch_, k, row_));
     return out;
 }
 

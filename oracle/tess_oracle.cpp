@@ -691,7 +691,15 @@ CellResult Diagram::compute(const Vec3& position, OptIdx self, SearchMode mode, 
     r.neighbors = polyhedron.compute_neighbors();    // interface.rs:342-344
     for (size_t f = 0; f < polyhedron.faces.len(); ++f)
         if (polyhedron.faces.has(f)) r.areas.push_back(0.5 * mag(polyhedron.weighted_normal(f)));  // interface.rs:408-410
-    if (want_vertices) r.vertices = polyhedron.compute_vertices();  // interface.rs:368-370
+    if (want_vertices) {
+        r.vertices = polyhedron.compute_vertices();  // interface.rs:368-370
+        for (size_t f = 0; f < polyhedron.faces.len(); ++f)
+            if (polyhedron.faces.has(f)) {  // VoronoiFace::compute_vertices (interface.rs:403-405)
+                const std::vector<Vec3> loop = polyhedron.compute_face_vertices(f);
+                r.face_loop_sizes.push_back(static_cast<uint32_t>(loop.size()));
+                r.face_loop_vertices.insert(r.face_loop_vertices.end(), loop.begin(), loop.end());
+            }
+    }
     r.max_radius_sq = polyhedron.max_vertex_radius_sq();
     r.counters.vertex_classifications = polyhedron.counters.vertex_classifications;
     r.counters.cuts = polyhedron.counters.cuts;

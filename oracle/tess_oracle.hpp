@@ -380,6 +380,8 @@ struct CellResult {
     std::vector<int64_t> neighbors;  // face-slot order; walls are -1..-6
     std::vector<double> areas;       // same order
     std::vector<Vec3> vertices;      // cell-local coordinates (optional)
+    std::vector<uint32_t> face_loop_sizes;  // per face (same order as neighbors): vertices of its loop (optional)
+    std::vector<Vec3> face_loop_vertices;   // the loops, concatenated: compute_face_vertices (polyhedron.rs:897-919)
     uint32_t status = 0;
     double max_radius_sq = 0;        // final max |v|^2
     CellCounters counters;

@@ -22,6 +22,8 @@ struct OrcResult {
     std::vector<double> max_radius_sq;
     std::vector<uint64_t> vertex_offsets;  // m+1 (only when vertices requested)
     std::vector<double> vertices;          // xyz triples, cell-local
+    std::vector<uint64_t> loop_offsets;    // per face (global face order), n_faces+1
+    std::vector<double> loop_vertices;     // xyz triples of the face loops
     uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 }  // namespace
@@ -164,6 +166,7 @@ void* orc_compute_cells(const void* dv, const uint64_t* ids, uint64_t m, int mod
             r->face_offsets[c + 1] = r->face_offsets[c] + cells[c].neighbors.size();
             r->vertex_offsets[c + 1] = r->vertex_offsets[c] + cells[c].vertices.size();
         }
+        r->loop_offsets.assign(1, 0);
         r->neighbors.reserve(r->face_offsets[m]);
         r->areas.reserve(r->face_offsets[m]);
         r->vertices.reserve(3 * r->vertex_offsets[m]);
@@ -176,6 +179,10 @@ void* orc_compute_cells(const void* dv, const uint64_t* ids, uint64_t m, int mod
             r->areas.insert(r->areas.end(), cr.areas.begin(), cr.areas.end());
             for (const Vec3& v : cr.vertices) {
                 r->vertices.push_back(v.x); r->vertices.push_back(v.y); r->vertices.push_back(v.z);
+            }
+            for (uint32_t sz : cr.face_loop_sizes) r->loop_offsets.push_back(r->loop_offsets.back() + sz);
+            for (const Vec3& v : cr.face_loop_vertices) {
+                r->loop_vertices.push_back(v.x); r->loop_vertices.push_back(v.y); r->loop_vertices.push_back(v.z);
             }
             r->counters[0] += cr.counters.visited;
             r->counters[1] += cr.counters.tested;
@@ -227,6 +234,9 @@ const double* orc_result_max_radius_sq(const void* r) { return static_cast<const
 const uint64_t* orc_result_vertex_offsets(const void* r) { return static_cast<const OrcResult*>(r)->vertex_offsets.data(); }
 const double* orc_result_vertices(const void* r) { return static_cast<const OrcResult*>(r)->vertices.data(); }
 const uint64_t* orc_result_counters(const void* r) { return static_cast<const OrcResult*>(r)->counters; }
+uint64_t orc_result_n_loops(const void* r) { return static_cast<const OrcResult*>(r)->loop_offsets.size(); }
+const uint64_t* orc_result_loop_offsets(const void* r) { return static_cast<const OrcResult*>(r)->loop_offsets.data(); }
+const double* orc_result_loop_vertices(const void* r) { return static_cast<const OrcResult*>(r)->loop_vertices.data(); }
 
 // ---------------------------------------------------------------- unit hooks ---------------
 // vector3.rs

@@ -38,8 +38,18 @@ int main(int argc, char** argv) {
             total += v;
             if (i % 500 == 7) {
                 std::printf("cell %zu volume %.17g faces", i, v);
-                for (const tess::VoronoiFace& f : cell.compute_faces()) std::printf(" %lld:%.17g", (long long)f.compute_neighbor(), f.compute_area());
+                size_t loop_total = 0;
+                for (const tess::VoronoiFace& f : cell.compute_faces()) {
+                    std::printf(" %lld:%.17g", (long long)f.compute_neighbor(), f.compute_area());
+                    loop_total += f.compute_vertices().size();
+                }
                 std::printf("\n");
+                // Euler: sum of face loop lengths = 2E, V - E + F = 2
+                const size_t V = cell.compute_vertices().size(), F = cell.compute_faces().size();
+                if (loop_total % 2 != 0 || V + F != loop_total / 2 + 2) {
+                    std::printf("ERROR: Euler characteristic violated for cell %zu (V=%zu F=%zu 2E=%zu)\n", i, V, F, loop_total);
+                    return 3;
+                }
             }
         }
         std::printf("total %.17g\n", total);

@@ -80,6 +80,9 @@ def lib() -> C.CDLL:
         ("orc_result_vertices", f64), ("orc_result_counters", u64),
     ):
         sig(n, C.POINTER(t), vp)
+    sig("orc_result_n_loops", u64, vp)
+    sig("orc_result_loop_offsets", C.POINTER(u64), vp)
+    sig("orc_result_loop_vertices", C.POINTER(f64), vp)
     sig("orc_dot", f64, _f64p, _f64p)
     for n in ("orc_cross", "orc_add", "orc_sub"):
         sig(n, None, _f64p, _f64p, _f64p)
@@ -150,6 +153,10 @@ class CellResults:
         self.vertex_offsets = arr(L.orc_result_vertex_offsets(handle), m + 1, np.uint64).astype(np.int64)
         nv = int(self.vertex_offsets[-1])
         self.vertices = arr(L.orc_result_vertices(handle), 3 * nv, np.float64).reshape(nv, 3)
+        nlo = int(L.orc_result_n_loops(handle))
+        self.loop_offsets = arr(L.orc_result_loop_offsets(handle), nlo, np.uint64).astype(np.int64)
+        nlv = int(self.loop_offsets[-1]) if nlo else 0
+        self.loop_vertices = arr(L.orc_result_loop_vertices(handle), 3 * nlv, np.float64).reshape(nlv, 3)
         c = arr(L.orc_result_counters(handle), 8, np.uint64)
         self.counters = dict(
             visited=int(c[0]), tested=int(c[1]), vertex_classifications=int(c[2]), cuts=int(c[3]),
@@ -165,6 +172,10 @@ class CellResults:
 
     def cell_vertices(self, c: int) -> np.ndarray:
         return self.vertices[self.vertex_offsets[c]:self.vertex_offsets[c + 1]]
+
+    def face_loop(self, k: int) -> np.ndarray:
+        """Ordered vertices of global face k (needs want_vertices=True)."""
+        return self.loop_vertices[self.loop_offsets[k]:self.loop_offsets[k + 1]]
 
 
 class Diagram:

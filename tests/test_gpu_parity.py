@@ -399,3 +399,34 @@ def test_config2_one_million_uniform(tess, gen, ob):
 
 def test_config3_ten_million_uniform(tess, gen, ob):
     _full_size_checks(tess, gen, ob, gen.uniform(10_000_000, 3), 72, 5_000)
+
+
+# ------------------------------------------------------------------ geometry ---
+def test_vertices_and_face_loops_match_oracle(tess, gen, ob):
+    """Cell::compute_vertices (interface.rs:368) and VoronoiFace::compute_vertices (interface.rs:403 ->
+    polyhedron.rs:897-919): per-face ordered vertex loops, bit-identical coordinates and order; the cell's
+    vertex list is the same set (its order follows the vertex slots, which the kernel numbers differently)."""
+    u = gen.uniform(200, 54)
+    th, ph = np.arccos(2 * u[:, 0] - 1), 2 * np.pi * u[:, 1]
+    shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
+    bg = gen.uniform(6000, 64)
+    pts = np.concatenate([[[0.5, 0.5, 0.5]], shell, bg[np.linalg.norm(bg - 0.5, axis=1) > 0.35]])  # cell 0 needs the large-cell path
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=1 | 2 | 4 | 8)
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY, want_vertices=True)
+    helpers.assert_cells_identical(b, r, what="geometry run")
+    assert np.array_equal(b.vertex_offsets, r.vertex_offsets)
+    assert np.array_equal(b.face_vertex_offsets, r.loop_offsets)
+    assert len(r.cell_neighbors(0)) > 60
+    fo = b.face_offsets
+    for c in list(range(0, len(pts), 97)) + [0]:
+        assert {tuple(v) for v in b.cell_vertices(c)} == {tuple(v) for v in r.cell_vertices(c)}
+        for k in range(fo[c], fo[c + 1]):
+            assert np.array_equal(b.face_vertices(c, k), r.face_loop(k)), (c, k)
+    # the per-cell API
+    box = tess.Polyhedron(*BOX)
+    cell = d.get_cell_at_index(5, box)
+    faces = cell.compute_faces()
+    for j, f in enumerate(faces):
+        assert np.array_equal(f.compute_vertices(), r.face_loop(fo[5] + j))
+    d.close()

@@ -29,6 +29,7 @@ SYMBOLS = (
     "tess_diagram_copy_grid", "tess_diagram_copy_search_order", "tess_compute_all", "tess_compute_at_points",
     "tess_result_free", "tess_result_n_cells", "tess_result_volumes", "tess_result_face_offsets", "tess_result_neighbors",
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
+    "tess_result_face_vertex_offsets", "tess_result_face_vertex_indices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
     "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs",
     "tess_find_neighbors", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
@@ -118,7 +119,8 @@ def lib() -> C.CDLL:
     sig("tess_result_free", None, vp)
     sig("tess_result_n_cells", ci, vp, P(u64), P(u64))
     for n in ("tess_result_volumes", "tess_result_face_offsets", "tess_result_neighbors", "tess_result_areas", "tess_result_status",
-              "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices"):
+              "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices", "tess_result_face_vertex_offsets",
+              "tess_result_face_vertex_indices"):
         sig(n, ci, vp, P(vp))
     sig("tess_result_counters", ci, vp, P(u64 * 8))
     sig("tess_result_volume_sum", ci, vp, P(f64))

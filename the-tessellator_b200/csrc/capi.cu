@@ -196,7 +196,7 @@ struct tess_diagram {
 struct tess_result {
     int device = 0;
     cudaStream_t stream = nullptr;  // stream the arrays were allocated on (stream-ordered allocator)
-    uint64_t n_cells = 0, n_faces = 0, n_vertices = 0;
+    uint64_t n_cells = 0, n_faces = 0, n_vertices = 0, n_loop_entries = 0;
     // device arrays (cudaMallocAsync on `stream`: cached by the device's memory pool between steps)
     double* vol = nullptr;
     uint32_t* nfaces = nullptr;
@@ -207,19 +207,23 @@ struct tess_result {
     double* area = nullptr;
     uint32_t* nverts = nullptr;
     uint64_t* voffsets = nullptr;
+    uint64_t* fv_offsets = nullptr;  // per face: start of its vertex loop (n_faces+1)
+    uint32_t* fv_idx = nullptr;      // loop entries: rank of the vertex in the cell's vertex list
     double* vtx = nullptr;
     unsigned long long* counters = nullptr;
     unsigned long long counters_redo[CNT_N] = {0, 0, 0, 0, 0, 0, 0, 0};  // work done by the large-cell pass
     double ms_clip = 0, ms_redo = 0, ms_outputs = 0, ms_total = 0;  // CUDA-event durations on the launching stream
     // host copies
     std::vector<double> h_vol, h_area, h_vtx;
-    std::vector<uint64_t> h_offsets, h_voffsets;
+    std::vector<uint64_t> h_offsets, h_voffsets, h_fv_offsets;
+    std::vector<uint32_t> h_fv_idx;
+    bool have_fvo = false, have_fvi = false;
     std::vector<int64_t> h_nbr, h_cell_id;
     std::vector<uint32_t> h_status;
     bool have_vol = false, have_area = false, have_offsets = false, have_nbr = false, have_ids = false, have_status = false, have_voff = false, have_vtx = false;
     ~tess_result() {
         cudaSetDevice(device);
-        for (void* p : {(void*)vol, (void*)nfaces, (void*)status, (void*)cell_id, (void*)offsets, (void*)nbr, (void*)area, (void*)nverts, (void*)voffsets, (void*)vtx, (void*)counters})
+        for (void* p : {(void*)vol, (void*)nfaces, (void*)status, (void*)cell_id, (void*)offsets, (void*)nbr, (void*)area, (void*)nverts, (void*)voffsets, (void*)vtx, (void*)counters, (void*)fv_offsets, (void*)fv_idx})
             if (p) cudaFreeAsync(p, stream);
     }
 };
@@ -610,10 +614,21 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
 
     Scratch tmp(s);
     const uint32_t fstride = 40;  // output capacity of the small path; larger cells go to the large path
-    const uint32_t vstride = clip_small_vmax();
+    // geometry pools (TESS_OUT_VERTICES): room for 48 vertices / 144 loop entries per cell on average
+    // (uniform input needs 27 / 81); exceeding it is reported, never silently truncated
+    const unsigned long long gv_cap = want_vtx ? (unsigned long long)n_rows * 48ull + 4096ull : 0ull;
+    const unsigned long long gl_cap = want_vtx ? (unsigned long long)n_rows * 144ull + 16384ull : 0ull;
+    double* gv_xyz = want_vtx ? tmp.get<double>(3 * gv_cap) : nullptr;
+    uint32_t* gl_idx = want_vtx ? tmp.get<uint32_t>(gl_cap) : nullptr;
+    unsigned long long* g_cursor = tmp.get<unsigned long long>(2);
+    uint32_t* nloops = want_vtx ? tmp.get<uint32_t>(n_rows) : nullptr;
+    unsigned long long* vbase = want_vtx ? tmp.get<unsigned long long>(n_rows) : nullptr;
+    unsigned long long* lbase = want_vtx ? tmp.get<unsigned long long>(n_rows) : nullptr;
+    uint16_t* st_flen = want_vtx ? tmp.get<uint16_t>(n_rows * fstride) : nullptr;
+    TESS_CUDA_CHECK(cudaMemsetAsync(g_cursor, 0, sizeof(unsigned long long) * 2, s));
+    if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(nloops, 0, sizeof(uint32_t) * n_rows, s));
     int64_t* st_nbr = tmp.get<int64_t>(n_rows * fstride);
     double* st_area = want_area ? tmp.get<double>(n_rows * fstride) : nullptr;
-    double* st_vtx = want_vtx ? tmp.get<double>(n_rows * (size_t)vstride * 3) : nullptr;
     uint32_t* ctrl = tmp.get<uint32_t>(16);  // [0] work counter, [1] n_failed, [2]/[3] n_failed of the redo passes, [5] table-only failures
     uint32_t* failed = tmp.get<uint32_t>(n_rows);
     double* query_dev = nullptr;
@@ -647,7 +662,8 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.row_base = d->own_slot_begin;
     P.vol = r->vol; P.nfaces = r->nfaces; P.status = r->status; P.cell_id = r->cell_id;
     P.st_nbr = st_nbr; P.st_area = st_area; P.fstride = fstride; P.stage_by_work = 0;
-    P.st_vtx = st_vtx; P.nverts = r->nverts; P.vstride = vstride;
+    P.gv_xyz = gv_xyz; P.gl_idx = gl_idx; P.gv_cap = gv_cap; P.gl_cap = gl_cap; P.g_cursor = g_cursor;
+    P.nverts = r->nverts; P.nloops = nloops; P.vbase = vbase; P.lbase = lbase; P.st_flen = st_flen;
     P.counters = want_cnt ? r->counters : nullptr;
     P.work_counter = ctrl;
     P.failed_slots = query ? nullptr : failed;
@@ -682,6 +698,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     uint32_t n_redo = 0, n_redo_b = 0;
     int64_t *sa_nbr = nullptr, *lg_nbr = nullptr;
     double *sa_area = nullptr, *lg_area = nullptr;
+    uint16_t *sa_flen = nullptr, *lg_flen = nullptr;
     uint32_t* failed_b = nullptr;
     const uint32_t lstride = clip_large_fmax();
     if (n_failed > 0) {
@@ -696,6 +713,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         } else {
         sa_nbr = tmp.get<int64_t>((size_t)n_redo * fstride);
         sa_area = want_area ? tmp.get<double>((size_t)n_redo * fstride) : nullptr;
+        sa_flen = want_vtx ? tmp.get<uint16_t>((size_t)n_redo * fstride) : nullptr;
         failed_b = tmp.get<uint32_t>(n_redo);
         {
             const ShellTable& t2 = d->table(R, s);
@@ -705,8 +723,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.table_full = t2.full ? 1u : 0u;
             Q.n_work = n_redo;
             Q.work_slots = failed;
-            Q.st_nbr = sa_nbr; Q.st_area = sa_area; Q.fstride = fstride; Q.stage_by_work = 1;
-            Q.st_vtx = nullptr;  // vertices of redone cells are not staged (TESS_OUT_VERTICES covers first-pass cells)
+            Q.st_nbr = sa_nbr; Q.st_area = sa_area; Q.st_flen = sa_flen; Q.fstride = fstride; Q.stage_by_work = 1;
             Q.failed_slots = failed_b;
             Q.n_failed = ctrl + 2;
             Q.failed_cap = n_redo;
@@ -721,6 +738,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             if (n_redo_b > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
             lg_nbr = tmp.get<int64_t>((size_t)n_redo_b * lstride);
             lg_area = want_area ? tmp.get<double>((size_t)n_redo_b * lstride) : nullptr;
+            lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)n_redo_b * lstride) : nullptr;
             uint32_t* failed_c = tmp.get<uint32_t>(n_redo_b);
             unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
             for (int attempt = 0; attempt < 12; ++attempt) {
@@ -731,8 +749,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
                 Q.table_full = t2.full ? 1u : 0u;
                 Q.n_work = n_redo_b;
                 Q.work_slots = failed_b;
-                Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.fstride = lstride; Q.stage_by_work = 1;
-                Q.st_vtx = nullptr;
+                Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.st_flen = lg_flen; Q.fstride = lstride; Q.stage_by_work = 1;
                 Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
                 if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
                 Q.failed_slots = failed_c;
@@ -765,19 +782,32 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     r->n_faces = total;
     r->nbr = dmalloc<int64_t>(total, s);
     if (want_area) r->area = dmalloc<double>(total, s);
-    launch_compact_faces(r->status, r->offsets, st_nbr, st_area, fstride, n_rows, r->nbr, r->area, s);
+    uint32_t* flen_csr = want_vtx ? tmp.get<uint32_t>(total + 1) : nullptr;
+    if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(flen_csr + total, 0, sizeof(uint32_t), s));
+    launch_compact_faces(r->status, r->offsets, st_nbr, st_area, st_flen, fstride, n_rows, r->nbr, r->area, flen_csr, s);
     if (n_redo)  // pass A rows (rows redone again by pass B are overwritten right after)
-        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, sa_nbr, sa_area, fstride, n_redo, r->nbr, r->area, s);
+        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, sa_nbr, sa_area, sa_flen, fstride, n_redo, r->nbr, r->area, flen_csr, s);
     if (n_redo_b)
-        launch_compact_redo(failed_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lstride, n_redo_b, r->nbr, r->area, s);
+        launch_compact_redo(failed_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lg_flen, lstride, n_redo_b, r->nbr, r->area, flen_csr, s);
     if (want_vtx) {
+        unsigned long long used[2] = {0, 0};
+        TESS_CUDA_CHECK(cudaMemcpyAsync(used, g_cursor, sizeof(used), cudaMemcpyDeviceToHost, s));
         launch_exclusive_scan_u32_to_u64(r->nverts, r->voffsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
-        uint64_t tv = 0;
+        uint64_t tv = 0, tl = 0;
         TESS_CUDA_CHECK(cudaMemcpyAsync(&tv, r->voffsets + n_rows, sizeof(tv), cudaMemcpyDeviceToHost, s));
+        r->fv_offsets = dmalloc<uint64_t>(total + 1, s);
+        void* scan_tmp2 = tmp.get<char>(scan_tmp_bytes(total + 1));
+        launch_exclusive_scan_u32_to_u64(flen_csr, r->fv_offsets, total + 1, scan_tmp2, scan_tmp_bytes(total + 1), s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(&tl, r->fv_offsets + total, sizeof(tl), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (used[0] > gv_cap || used[1] > gl_cap)
+            return fail(TESS_ERR_CAPACITY, "TESS_OUT_VERTICES: the cells have more vertices / face-loop entries than the geometry pools hold (48 / 144 per cell on average)");
         r->n_vertices = tv;
+        r->n_loop_entries = tl;
         r->vtx = dmalloc<double>(3 * tv, s);
-        launch_compact_vertices(r->nverts, r->voffsets, st_vtx, vstride, n_rows, r->vtx, s);
+        r->fv_idx = dmalloc<uint32_t>(tl, s);
+        launch_gather_vertices(r->nverts, vbase, r->voffsets, gv_xyz, n_rows, r->vtx, s);
+        launch_gather_loops(nloops, lbase, r->offsets, r->fv_offsets, gl_idx, n_rows, r->fv_idx, s);
     }
     TESS_CUDA_CHECK(cudaEventRecord(ev[3], s));
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -866,6 +896,8 @@ int tess_result_areas(tess_result* r, const double** out) { return host_view(r, 
 int tess_result_cell_ids(tess_result* r, const int64_t** out) { return host_view(r, r ? r->cell_id : nullptr, r ? r->n_cells : 0, r->h_cell_id, r->have_ids, out); }
 int tess_result_vertex_offsets(tess_result* r, const uint64_t** out) { return host_view(r, r ? r->voffsets : nullptr, r ? r->n_cells + 1 : 0, r->h_voffsets, r->have_voff, out); }
 int tess_result_vertices(tess_result* r, const double** out) { return host_view(r, r ? r->vtx : nullptr, r ? 3 * r->n_vertices : 0, r->h_vtx, r->have_vtx, out); }
+int tess_result_face_vertex_offsets(tess_result* r, const uint64_t** out) { return host_view(r, r ? r->fv_offsets : nullptr, r ? r->n_faces + 1 : 0, r->h_fv_offsets, r->have_fvo, out); }
+int tess_result_face_vertex_indices(tess_result* r, const uint32_t** out) { return host_view(r, r ? r->fv_idx : nullptr, r ? r->n_loop_entries : 0, r->h_fv_idx, r->have_fvi, out); }
 
 int tess_result_status(tess_result* r, const uint32_t** out) {
     const bool first = r && !r->have_status;

@@ -166,6 +166,8 @@ struct WarpSmem {
     double4 cand_plane[32];
     long long cand_id[32];
     double cpos[4];                          // position of the cell's particle (kept here, not in registers)
+    uint16_t flen[Cfg::FMAX];                // geometry output: loop length / loop offset per face slot
+    uint16_t floff[Cfg::FMAX];
     // masks of the large configuration live here (1-word placeholders otherwise)
     uint32_t m_vlive[Cfg::REG ? 1 : Cfg::VMAX / 32], m_vbefore[Cfg::REG ? 1 : Cfg::VMAX / 32], m_inside[Cfg::REG ? 1 : Cfg::VMAX / 32],
         m_outside[Cfg::REG ? 1 : Cfg::VMAX / 32], m_removed[Cfg::REG ? 1 : Cfg::VMAX / 32];
@@ -1059,6 +1061,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                         wn = add(wn, cross(prev, cur));
                         e = MeshT::e_next(w);
                     }
+                    if (P.gv_xyz) sm->flen[f] = (uint16_t)(guard + 2);      // vertices of this face's loop
                     const double area = mul(0.5, __dsqrt_rn(dot(wn, wn)));  // interface.rs:408-410
                     contrib = dot(A, wn);                                    // polyhedron.rs:849
                     const uint32_t rank = rank_base + __popc(lw & ((1u << lane) - 1u));
@@ -1075,23 +1078,99 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
             if (nf > P.fstride) status |= ST_CAPACITY_OVERFLOW;
         }
         // volume = (sum over faces) / 6 (polyhedron.rs:854)
-        if (P.st_vtx && !failed) {
-            uint32_t vb = 0;
+        // ---- geometry (TESS_OUT_VERTICES): Cell::compute_vertices (interface.rs:368-370) and
+        //      VoronoiFace::compute_vertices (interface.rs:403-405 -> polyhedron.rs:897-919) ----------
+        if (P.gv_xyz && !failed && (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) == 0) {
+            __syncwarp();
+            // rank of a vertex slot in the cell's vertex list (ascending slot order)
+            uint32_t nv = 0;
+            if constexpr (!Cfg::REG) {
+                for (int p0 = 0; p0 < M.nwv(); p0 += 32) {  // exclusive prefix of the per-word populations
+                    const int p = p0 + lane;
+                    uint32_t c = p < M.nwv() ? __popc(sm->m_vlive[p]) : 0u, inc = c;
 #pragma unroll
-            for (int p = 0; p < MeshT::NWV; ++p) {
-                if (p >= M.nwv()) break;
-                const uint32_t lw = M.vlive.word(p);
-                if ((lw >> lane) & 1u) {
-                    const uint32_t r = vb + __popc(lw & ((1u << lane) - 1u));
-                    if (r < P.vstride) {
-                        double* o = P.st_vtx + (srow * P.vstride + r) * 3;
-                        o[0] = sm->vx[32 * p + lane]; o[1] = sm->vy[32 * p + lane]; o[2] = sm->vz[32 * p + lane];
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t u = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += u;
+                    }
+                    if (p < M.nwv()) sm->m_removed[p] = nv + inc - c;
+                    nv += __shfl_sync(FULL, inc, 31);
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int p = 0; p < MeshT::NWV; ++p) nv += __popc(M.vlive.word(p));
+            }
+            auto vrank = [&](uint32_t v) -> uint32_t {
+                if constexpr (Cfg::REG) {
+                    uint32_t r = __popc(M.vlive.word(0) & (v < 32u ? (1u << v) - 1u : 0xFFFFFFFFu));
+                    if (MeshT::NWV > 1 && v >= 32u) r += __popc(M.vlive.word(1) & ((1u << (v - 32u)) - 1u));
+                    return r;
+                } else {
+                    return sm->m_removed[v >> 5] + __popc(sm->m_vlive[v >> 5] & ((1u << (v & 31u)) - 1u));
+                }
+            };
+            // loop offsets of the faces in slot order
+            uint32_t nl = 0;
+#pragma unroll
+            for (int q = 0; q < MeshT::NWF; ++q) {
+                if (q >= M.nwf()) break;
+                const uint32_t lw = M.flive.word(q);
+                const uint32_t c = ((lw >> lane) & 1u) ? sm->flen[32 * q + lane] : 0u;
+                uint32_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                if ((lw >> lane) & 1u) sm->floff[32 * q + lane] = (uint16_t)(nl + inc - c);
+                nl += __shfl_sync(FULL, inc, 31);
+            }
+            unsigned long long vb = 0, lb = 0;
+            if (lane == 0) {
+                vb = atomicAdd(&P.g_cursor[0], (unsigned long long)nv);
+                lb = atomicAdd(&P.g_cursor[1], (unsigned long long)nl);
+                P.nverts[row] = nv;
+                P.nloops[row] = nl;
+                P.vbase[row] = vb;
+                P.lbase[row] = lb;
+            }
+            vb = __shfl_sync(FULL, vb, 0);
+            lb = __shfl_sync(FULL, lb, 0);
+            if (vb + nv <= P.gv_cap && lb + nl <= P.gl_cap) {  // otherwise the host sees the cursors and reports
+#pragma unroll
+                for (int p = 0; p < MeshT::NWV; ++p) {
+                    if (p >= M.nwv()) break;
+                    const uint32_t lw = M.vlive.word(p);
+                    if ((lw >> lane) & 1u) {
+                        const uint32_t v = 32 * p + lane;
+                        double* o = P.gv_xyz + (vb + vrank(v)) * 3;
+                        o[0] = sm->vx[v]; o[1] = sm->vy[v]; o[2] = sm->vz[v];
                     }
                 }
-                vb += __popc(lw);
+                uint32_t frank_base = 0;
+#pragma unroll
+                for (int q = 0; q < MeshT::NWF; ++q) {
+                    if (q >= M.nwf()) break;
+                    const uint32_t lw = M.flive.word(q);
+                    if ((lw >> lane) & 1u) {
+                        const int f = 32 * q + lane;
+                        // compute_face_vertices (polyhedron.rs:897-919): targets from the starting edge on
+                        uint32_t* o = P.gl_idx + lb + sm->floff[f];
+                        const uint32_t s0 = sm->fstart[f];
+                        uint32_t e = s0;
+                        int guard = 0;
+                        do {
+                            const EW w = sm->edge[e];
+                            *o++ = vrank(MeshT::e_tgt(w));
+                            e = MeshT::e_next(w);
+                        } while (e != s0 && ++guard < Cfg::EMAX);
+                        const uint32_t rank = frank_base + __popc(lw & ((1u << lane) - 1u));
+                        if (rank < P.fstride) P.st_flen[srow * P.fstride + rank] = sm->flen[f];
+                    }
+                    frank_base += __popc(lw);
+                }
             }
-            if (lane == 0) P.nverts[row] = vb < P.vstride ? vb : P.vstride;
-            if (vb > P.vstride) status |= ST_CAPACITY_OVERFLOW;
         }
         if (lane == 0) {
             // cells this configuration cannot finish are queued for the large-cell / larger-table pass
@@ -1105,7 +1184,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
             const bool empty = (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) != 0;
             P.vol[row] = empty ? 0.0 : __ddiv_rn(vol_part, 6.0);
             P.nfaces[row] = empty ? 0u : nf;
-            if (P.st_vtx && empty) P.nverts[row] = 0u;
+            if (P.gv_xyz && empty) { P.nverts[row] = 0u; P.nloops[row] = 0u; }
             P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
             if (P.cell_id) P.cell_id[row] = self_id;
         }

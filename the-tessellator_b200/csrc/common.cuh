@@ -72,10 +72,17 @@ struct ClipParams {
     double* st_area;
     uint32_t fstride;
     uint32_t stage_by_work;
-    // optional vertex staging, same indexing: [..][vstride][3]
-    double* st_vtx;                // nullable
-    uint32_t* nverts;
-    uint32_t vstride;
+    // optional geometry outputs (TESS_OUT_VERTICES): each cell bump-allocates room for its
+    // vertices and its face loops in two pools; they are gathered into CSR order afterwards
+    double* gv_xyz;                // nullable; vertex pool, xyz triples (cell-local coordinates)
+    uint32_t* gl_idx;              // face-loop pool: per face, the ranks of its vertices in the cell's vertex list
+    unsigned long long gv_cap, gl_cap;
+    unsigned long long* g_cursor;  // [0] vertices handed out, [1] loop entries handed out
+    uint32_t* nverts;              // per row
+    uint32_t* nloops;
+    unsigned long long* vbase;
+    unsigned long long* lbase;
+    uint16_t* st_flen;             // per staged face: loop length (indexed like st_nbr)
     unsigned long long* counters;  // CNT_N, nullable
     uint32_t* work_counter;        // dynamic work distribution
     // cells this configuration could not finish (capacity / table exhausted): slots appended here
@@ -134,9 +141,10 @@ uint32_t clip_large_fmax();
 uint32_t clip_large_vmax();
 
 void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t n, void* tmp, size_t tmp_bytes, cudaStream_t s);
-void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_rows, int64_t* nbr, double* area, cudaStream_t s);
-void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, cudaStream_t s);
-void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s);
+void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s);
+void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s);
+void launch_gather_vertices(const uint32_t* nverts, const unsigned long long* vbase, const uint64_t* voffsets, const double* pool, size_t n_rows, double* vtx, cudaStream_t s);
+void launch_gather_loops(const uint32_t* nloops, const unsigned long long* lbase, const uint64_t* face_offsets, const uint64_t* fv_offsets, const uint32_t* pool, size_t n_rows, uint32_t* out, cudaStream_t s);
 void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s);
 double measure_fp64_peak_tflops();
 void launch_radius_query(const QueryParams& p, bool fill, cudaStream_t s);

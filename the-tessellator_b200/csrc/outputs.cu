@@ -16,8 +16,9 @@ constexpr int kRowsPerBlock = 256;
 // One block packs kRowsPerBlock consecutive rows: every thread walks output positions and finds
 // the owning row by binary search in the block's slice of the offsets.
 __global__ void __launch_bounds__(256) compact_faces_kernel(const uint32_t* __restrict__ status, const uint64_t* __restrict__ offsets,
-                                                            const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area, uint32_t fstride,
-                                                            size_t n_rows, int64_t* __restrict__ nbr, double* __restrict__ area) {
+                                                            const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area,
+                                                            const uint16_t* __restrict__ st_flen, uint32_t fstride, size_t n_rows,
+                                                            int64_t* __restrict__ nbr, double* __restrict__ area, uint32_t* __restrict__ flen) {
     __shared__ uint64_t s_off[kRowsPerBlock + 1];
     const size_t row0 = (size_t)blockIdx.x * kRowsPerBlock;
     const int rows = (int)min((size_t)kRowsPerBlock, n_rows - row0);
@@ -35,14 +36,16 @@ __global__ void __launch_bounds__(256) compact_faces_kernel(const uint32_t* __re
         const uint32_t k = (uint32_t)(p - s_off[lo]);
         nbr[p] = st_nbr[row * fstride + k];
         if (area) area[p] = st_area[row * fstride + k];
+        if (flen) flen[p] = st_flen[row * fstride + k];
     }
 }
 
 // Rows recomputed by the large-cell pass: one warp per work item, staging indexed by work item.
 __global__ void __launch_bounds__(128) compact_redo_kernel(const uint32_t* __restrict__ work_slots, const uint32_t* __restrict__ row_of_slot, uint32_t row_base,
                                                            const uint32_t* __restrict__ nfaces, const uint64_t* __restrict__ offsets,
-                                                           const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area, uint32_t fstride,
-                                                           size_t n_work, int64_t* __restrict__ nbr, double* __restrict__ area) {
+                                                           const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area,
+                                                           const uint16_t* __restrict__ st_flen, uint32_t fstride, size_t n_work,
+                                                           int64_t* __restrict__ nbr, double* __restrict__ area, uint32_t* __restrict__ flen) {
     const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_work) return;
@@ -53,17 +56,32 @@ __global__ void __launch_bounds__(128) compact_redo_kernel(const uint32_t* __res
     for (uint32_t k = lane; k < nf; k += 32) {
         nbr[o + k] = st_nbr[w * fstride + k];
         if (area) area[o + k] = st_area[w * fstride + k];
+        if (flen) flen[o + k] = st_flen[w * fstride + k];
     }
 }
 
-__global__ void __launch_bounds__(256) compact_vertices_kernel(const uint32_t* __restrict__ nverts, const uint64_t* __restrict__ offsets,
-                                                               const double* __restrict__ st_vtx, uint32_t vstride, size_t n_rows, double* __restrict__ vtx) {
+// Geometry outputs: one warp copies one row's block out of the bump-allocated pools.
+__global__ void __launch_bounds__(256) gather_vertices_kernel(const uint32_t* __restrict__ nverts, const unsigned long long* __restrict__ vbase,
+                                                              const uint64_t* __restrict__ voffsets, const double* __restrict__ pool, size_t n_rows,
+                                                              double* __restrict__ vtx) {
     const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= n_rows) return;
     const uint32_t nv = nverts[w];
-    const uint64_t o = offsets[w];
-    for (uint32_t k = lane; k < 3 * nv; k += 32) vtx[3 * o + k] = st_vtx[w * (size_t)vstride * 3 + k];
+    const unsigned long long src = vbase[w];
+    const uint64_t dst = voffsets[w];
+    for (uint32_t k = lane; k < 3 * nv; k += 32) vtx[3 * dst + k] = pool[3 * src + k];
+}
+__global__ void __launch_bounds__(256) gather_loops_kernel(const uint32_t* __restrict__ nloops, const unsigned long long* __restrict__ lbase,
+                                                           const uint64_t* __restrict__ face_offsets, const uint64_t* __restrict__ fv_offsets,
+                                                           const uint32_t* __restrict__ pool, size_t n_rows, uint32_t* __restrict__ out) {
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    const uint32_t nl = nloops[w];
+    const unsigned long long src = lbase[w];
+    const uint64_t dst = fv_offsets[face_offsets[w]];
+    for (uint32_t k = lane; k < nl; k += 32) out[dst + k] = pool[src + k];
 }
 
 // Deterministic two-level sum (fixed block partition, fixed tree) so that repeated runs agree bitwise.
@@ -92,28 +110,38 @@ __global__ void volume_final_kernel(const double* __restrict__ partial, int nb, 
 
 }  // namespace
 
-void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_rows, int64_t* nbr,
-                          double* area, cudaStream_t s) {
+void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride,
+                          size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
-    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, fstride, n_rows, nbr, area);
+    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, st_flen, fstride, n_rows, nbr, area, flen);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets,
-                         const int64_t* st_nbr, const double* st_area, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, cudaStream_t s) {
+                         const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_work, int64_t* nbr, double* area,
+                         uint32_t* flen, cudaStream_t s) {
     if (!n_work) return;
     const unsigned int nb = (unsigned int)((n_work * 32 + 127) / 128);
-    compact_redo_kernel<<<nb, 128, 0, s>>>(work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, fstride, n_work, nbr, area);
+    compact_redo_kernel<<<nb, 128, 0, s>>>(work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, st_flen, fstride, n_work, nbr, area, flen);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_compact_vertices(const uint32_t* nverts, const uint64_t* offsets, const double* st_vtx, uint32_t vstride, size_t n_rows, double* vtx, cudaStream_t s) {
+void launch_gather_vertices(const uint32_t* nverts, const unsigned long long* vbase, const uint64_t* voffsets, const double* pool, size_t n_rows, double* vtx, cudaStream_t s) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
-    compact_vertices_kernel<<<nb, 256, 0, s>>>(nverts, offsets, st_vtx, vstride, n_rows, vtx);
+    gather_vertices_kernel<<<nb, 256, 0, s>>>(nverts, vbase, voffsets, pool, n_rows, vtx);
+    note_launch();
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_gather_loops(const uint32_t* nloops, const unsigned long long* lbase, const uint64_t* face_offsets, const uint64_t* fv_offsets, const uint32_t* pool, size_t n_rows,
+                         uint32_t* out, cudaStream_t s) {
+    if (!n_rows) return;
+    const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
+    gather_loops_kernel<<<nb, 256, 0, s>>>(nloops, lbase, face_offsets, fv_offsets, pool, n_rows, out);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }

@@ -106,6 +106,20 @@ class CellBatch:
         nv = int(self.vertex_offsets[-1])
         return self._view("tess_result_vertices", 3 * nv, np.float64).reshape(nv, 3)
 
+    @property
+    def face_vertex_offsets(self) -> np.ndarray:
+        return self._view("tess_result_face_vertex_offsets", self.n_faces + 1, np.uint64).astype(np.int64)
+
+    @property
+    def face_vertex_indices(self) -> np.ndarray:
+        return self._view("tess_result_face_vertex_indices", int(self.face_vertex_offsets[-1]), np.uint32)
+
+    def face_vertices(self, row: int, k: int) -> np.ndarray:
+        """Ordered vertex loop of global face k of cell `row`, cell-local coordinates (polyhedron.rs:897-919)."""
+        fo = self.face_vertex_offsets
+        idx = self.face_vertex_indices[fo[k]:fo[k + 1]].astype(np.int64)
+        return self.vertices[int(self.vertex_offsets[row]) + idx]
+
     def counters(self) -> dict:
         arr = (C.c_uint64 * 8)()
         check(_lib.lib().tess_result_counters(self._h, C.byref(arr)))
@@ -426,6 +440,10 @@ class VoronoiFace:
     def compute_neighbor(self) -> int:
         """interface.rs:413-416."""
         return int(self.cell._batch.neighbors[self._k])
+
+    def compute_vertices(self) -> np.ndarray:
+        """interface.rs:403-405: the face's vertices in loop order, cell-local coordinates."""
+        return self.cell._batch.face_vertices(self.cell._row, self._k).copy()
 
 
 def device_count() -> int:
