@@ -430,3 +430,30 @@ def test_vertices_and_face_loops_match_oracle(tess, gen, ob):
     for j, f in enumerate(faces):
         assert np.array_equal(f.compute_vertices(), r.face_loop(fo[5] + j))
     d.close()
+
+
+# ------------------------------------------------------------------ awkward inputs -----------
+@pytest.mark.parametrize("case", ["duplicates", "on_walls", "outside_box", "two_points", "collinear", "coplanar", "lattice_jitter0"])
+def test_awkward_inputs_match_oracle(tess, gen, ob, case):
+    """Inputs the reference does not guard against (exact duplicates give a NaN plane that cuts nothing,
+    SURVEY D16; particles on or outside the container; exact lattice ties).  Whatever the reference's
+    arithmetic does with them, the kernel must do the same, bit for bit, and flag the same cells."""
+    base = gen.uniform(3000, 81)
+    pts = {
+        "duplicates": lambda: np.concatenate([base, base[:200], base[:50]]),
+        "on_walls": lambda: np.concatenate([base, np.round(gen.uniform(400, 82), 0) * np.array([1, 1, 0]) + gen.uniform(400, 83) * np.array([0, 0, 1])]),
+        "outside_box": lambda: np.concatenate([base, 1.0 + 0.05 * gen.uniform(30, 84), -0.05 * gen.uniform(30, 85)]),
+        "two_points": lambda: np.array([[0.25, 0.5, 0.5], [0.75, 0.5, 0.5]]),
+        "collinear": lambda: np.stack([np.linspace(0.05, 0.95, 40), np.full(40, 0.5), np.full(40, 0.5)], axis=1),
+        "coplanar": lambda: np.concatenate([gen.uniform(500, 86) * np.array([1, 1, 0]) + np.array([0, 0, 0.5])]),
+        "lattice_jitter0": lambda: gen.bcc(6, 5, jitter=0.0),
+    }[case]()
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=ALL_OUT, table_radius=1 << 20)
+    r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
+    helpers.assert_cells_identical(b, r, what=case)
+    assert np.array_equal(b.status, r.status)
+    c = b.counters()
+    for k in ("tested", "cuts", "new_vertices", "faces", "degenerate_skips"):
+        assert c[k] == r.counters[k], k
+    d.close()
