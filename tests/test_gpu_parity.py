@@ -189,8 +189,10 @@ def test_results_are_deterministic(tess, gen):
 
 def test_parallel_cut_equals_serial_walk(tess, gen, tmp_path):
     """The kernel cuts in lane-parallel form when no vertex lies on the plane and falls back to the
-    reference-shaped serial walk otherwise.  TESS_FORCE_SERIAL=1 disables the fast path: both must
-    give bit-identical volumes, areas and face order."""
+    reference-shaped serial walk otherwise, and the fast path finds the crossed half-edges either
+    through the per-vertex adjacency lists or by sweeping the half-edge table.  TESS_FORCE_SERIAL=1
+    disables the fast path, TESS_FORCE_SWEEP=1 the adjacency lists: all three must give bit-identical
+    volumes, areas and face order."""
     import subprocess
     import sys
 
@@ -203,12 +205,13 @@ def test_parallel_cut_equals_serial_walk(tess, gen, tmp_path):
         "np.savez(sys.argv[1], v=b.volumes, n=b.neighbors, a=b.areas, o=b.face_offsets, s=b.status)"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for tag, env in (("par", {}), ("ser", {"TESS_FORCE_SERIAL": "1"})):
+    for tag, env in (("par", {}), ("ser", {"TESS_FORCE_SERIAL": "1"}), ("sweep", {"TESS_FORCE_SWEEP": "1"})):
         f = str(tmp_path / f"{tag}.npz")
         subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, **env))
         outs[tag] = np.load(f)
     for k in "vnaos":
         assert np.array_equal(outs["par"][k], outs["ser"][k]), k
+        assert np.array_equal(outs["par"][k], outs["sweep"][k]), k
 
 
 # ------------------------------------------------------------------ options ------------------

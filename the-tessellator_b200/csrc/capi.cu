@@ -670,7 +670,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.n_failed = ctrl + 1;
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
-    P.flags = std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u;
+    P.flags = (std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u) | (std::getenv("TESS_FORCE_SWEEP") ? 2u : 0u);
     cudaEvent_t ev[5];
     for (auto& e : ev) TESS_CUDA_CHECK(cudaEventCreate(&e));
     struct EvGuard {

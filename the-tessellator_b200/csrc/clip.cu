@@ -42,6 +42,9 @@ __constant__ uint32_t kCubeEdges[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x05020
                                         0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
                                         0x000211u, 0x040612u, 0x080713u, 0x0c0310u, 0x020015u, 0x0e0416u, 0x0a0517u, 0x060114u};
 
+// ... and, per cube vertex, the three half-edges that START there (source(e) = target(flip(e)))
+__constant__ unsigned char kCubeVout[24] = {2, 15, 21, 3, 6, 20, 0, 5, 17, 1, 12, 16, 11, 14, 22, 7, 10, 23, 4, 9, 18, 8, 13, 19};
+
 // ---------------------------------------------------------------------------------------------
 // Bit masks over table slots.  Small cells keep them in registers, large cells in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -162,6 +165,11 @@ struct WarpSmem {
     typename Cfg::Idx pred[32];              // crossing k -> the crossing that precedes it around the cut
     typename Cfg::Idx vfree[32];             // first free vertex slots
     uint8_t kof[Cfg::EMAX];                  // outgoing half-edge slot -> crossing index
+    typename Cfg::Idx ovl[32];               // the (first 32) Outside vertices of the current plane
+    // While every vertex is 3-valent (no plane has ever passed through a vertex of this cell) vout[3v..3v+2]
+    // are the half-edges that start at vertex v: a cut is then found from its Outside vertices, without
+    // sweeping the half-edge table.
+    typename Cfg::Idx vout[Cfg::REG ? 3 * Cfg::VMAX : 4];
     // candidate tile: bisector plane {n, offset} and id of the candidate each lane staged
     double4 cand_plane[32];
     long long cand_id[32];
@@ -195,6 +203,8 @@ struct Mesh {
     int f_top, f_hwm;  // same for faces: sm->fstack[0, f_top) + high-water mark (flive stays the iteration mask)
     // 32-slot words of the vertex / face tables that have ever been used (large cells sweep only these)
     int v_words, f_words;
+    bool simple;         // all vertices 3-valent and vout[] maintained (true until the serial walk first cuts)
+    uint32_t n_outside;  // Outside vertices of the last classification
     int lane;
     __device__ __forceinline__ int nwv() const { return Cfg::REG ? NWV : v_words; }
     __device__ __forceinline__ int nwf() const { return Cfg::REG ? NWF : f_words; }
@@ -259,6 +269,10 @@ struct Mesh {
         f_hwm = 6;
         v_words = 1;
         f_words = 1;
+        simple = Cfg::REG;
+        if constexpr (Cfg::REG) {
+            if (lane < 24) sm->vout[lane] = (Idx)kCubeVout[lane];
+        }
         __syncwarp();
         if (lane < 8) {
             // FDL FDR FUR FUL BDL BDR BUR BUL (polyhedron.rs:288-295); corner + (-p)
@@ -328,7 +342,7 @@ constexpr int CUT_FALLBACK = 3;
 // Returns 1 (cut), CUT_FALLBACK (let the serial walk decide) or -1 (table overflow).
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& cnt_nv) {
+__device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& cnt_nv, bool sweep_only) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
     using Idx = typename Cfg::Idx;
@@ -336,12 +350,48 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     const int lane = M.lane;
     const uint32_t lt = (1u << lane) - 1u;
 
-    // ---- 1. sweep the half-edge table ----------------------------------------------------------
-    const int n_pass = M.edge_passes();
-    if (n_pass > 32) return CUT_FALLBACK;  // deadbits holds one bit per pass
+    // ---- 1. find the outgoing half-edges (one per crossed face) and what dies ---------------------
     uint32_t K = 0;
-    uint32_t deadbits = 0;  // bit p: my half-edge of pass p dies
-    uint32_t keep_lo = 0, keep_hi = 0;  // faces my surviving half-edges belong to (FMAX <= 64 here)
+    uint32_t deadbits = 0;              // sweep variant: bit p = my half-edge of pass p dies
+    uint32_t keep_lo = 0, keep_hi = 0;  // sweep variant: faces my surviving half-edges belong to
+    uint32_t my_dead = Cfg::NONE;       // adjacency variant: the dying half-edge this lane found
+    uint32_t df_lo = 0, df_hi = 0;      //                    and the face it belongs to
+    int n_pass = 0;
+    bool adj = false;
+    if constexpr (Cfg::REG) adj = M.simple && !sweep_only && 3u * M.n_outside <= 32u;
+    if (adj) {
+        // 1a. every vertex is 3-valent and vout[] lists the half-edges leaving it: lane (i, j) takes
+        //     half-edge j of the i-th Outside vertex.  It either ends Outside too (it dies; so does its
+        //     flip, which the other vertex's lane finds) or ends Inside — then its flip is the outgoing
+        //     half-edge (Inside -> Outside) of a crossed face.
+        if constexpr (Cfg::REG) {
+            bool is_re = false;
+            uint32_t fl = 0;
+            if ((uint32_t)lane < 3u * M.n_outside) {
+                const uint32_t vi = (uint32_t)lane / 3u, j = (uint32_t)lane - 3u * vi;
+                const uint32_t e = sm->vout[3u * (uint32_t)sm->ovl[vi] + j];
+                const EW w = sm->edge[e];
+                fl = MeshT::e_flip(w);
+                if (M.outside.test(MeshT::e_tgt(w))) {
+                    my_dead = e;
+                    const uint32_t face = MeshT::e_face(w);
+                    if (face < 32u) df_lo = 1u << face; else df_hi = 1u << (face - 32u);
+                } else {
+                    is_re = true;
+                }
+            }
+            const uint32_t om = __ballot_sync(FULL, is_re);
+            if (is_re) {
+                const uint32_t k = __popc(om & lt);
+                sm->olist[k] = (Idx)fl;
+                sm->kof[fl] = (uint8_t)k;
+            }
+            K = __popc(om);
+        }
+    } else {
+    // 1b. sweep the half-edge table
+    n_pass = M.edge_passes();
+    if (n_pass > 32) return CUT_FALLBACK;  // deadbits holds one bit per pass
     for (int p = 0; p < n_pass; ++p) {
         const EW w = M.edge_of_pass(p);
         bool is_out = false, dead = false, keep = false;
@@ -372,6 +422,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
                 keep_lo = 1u;  // large cells: the face mask is rebuilt below, only if something died
             }
         }
+    }
     }
     if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
     __syncwarp();
@@ -473,6 +524,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     const uint32_t nv_pred = __shfl_sync(FULL, nv, (int)pk);  // previous_intersection (:550, :600)
     const uint32_t ck_pred = __shfl_sync(FULL, ck, (int)pk);
     const uint32_t ck0 = __shfl_sync(FULL, ck, (int)k0);
+    const uint32_t br_succ = __shfl_sync(FULL, br, (int)ks);
     uint32_t nb_lo = 0, nb_hi = 0;
     if (act) {
         const Vec3 a = {sm->vx[pv], sm->vy[pv], sm->vz[pv]};
@@ -487,6 +539,11 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         sm->fstart[f] = (Idx)o;                                       // :578-580
         if constexpr (Cfg::REG) {
             if (nv < 32u) nb_lo = 1u << nv; else nb_hi = 1u << (nv - 32u);
+            // the three half-edges leaving the new vertex: the re-entering one, the cap edge, and the
+            // bridge of the next crossed face
+            sm->vout[3u * nv] = (Idx)r;
+            sm->vout[3u * nv + 1u] = (Idx)ck;
+            sm->vout[3u * nv + 2u] = (Idx)br_succ;
         }
     }
     if (lane == 0) {
@@ -521,7 +578,34 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         M.note_vertex((int)__reduce_max_sync(FULL, act ? nv : 0u));
         __syncwarp();
     }
-    if (__any_sync(FULL, deadbits != 0u)) {
+    if (adj) {
+        if constexpr (Cfg::REG) {
+            const uint32_t dm = __ballot_sync(FULL, my_dead != Cfg::NONE);
+            if (dm) {
+                // Pool::remove in ascending slot order, as the sweep would do it
+                uint32_t rank = 0;
+                for (uint32_t m = dm; m; m &= m - 1u) rank += (__shfl_sync(FULL, my_dead, __ffs(m) - 1) < my_dead) ? 1u : 0u;
+                if (my_dead != Cfg::NONE) {
+                    sm->estack[M.e_top + rank] = (Idx)my_dead;
+                    sm->edge[my_dead] = MeshT::FREE_EDGE;
+                }
+                M.e_top += __popc(dm);
+                // faces of dying half-edges die unless the plane crosses them (then they hold an outgoing half-edge)
+                df_lo = __reduce_or_sync(FULL, df_lo);
+                df_hi = __reduce_or_sync(FULL, df_hi);
+                const uint32_t cr_lo = __reduce_or_sync(FULL, (act && f < 32u) ? 1u << f : 0u);
+                const uint32_t cr_hi = __reduce_or_sync(FULL, (act && f >= 32u) ? 1u << (f - 32u) : 0u);
+                const uint32_t d0 = df_lo & ~cr_lo & M.flive.word(0);
+                M.flive.set_word(0, M.flive.word(0) & ~d0);
+                M.retire_faces(0, d0);
+                if (MeshT::NWF > 1) {
+                    const uint32_t d1 = df_hi & ~cr_hi & M.flive.word(1);
+                    M.flive.set_word(1, M.flive.word(1) & ~d1);
+                    M.retire_faces(1, d1);
+                }
+            }
+        }
+    } else if (__any_sync(FULL, deadbits != 0u)) {
         const int old_top = M.e_top;
         for (int p = 0; p < n_pass; ++p) {
             const bool dead = (deadbits >> p) & 1u;
@@ -574,7 +658,8 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
 // Returns 0 = no cut, 1 = cut, 2 = skipped (D17), <0 = capacity overflow / inconsistency.
 // ---------------------------------------------------------------------------------------------
 template <class Cfg>
-__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv, bool serial_only) {
+__device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv, bool serial_only,
+                              bool sweep_only) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
     WarpSmem<Cfg>* sm = M.sm;
@@ -583,7 +668,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     // ---- classify every live vertex (find_outgoing_edge's vertex scan, polyhedron.rs:399-405,
     //      and every later vector_location call of the walk) --------------------------------------
     uint32_t any_out = 0, any_incident = 0;
-    uint32_t nlive = 0;
+    uint32_t nlive = 0, n_out = 0;
 #pragma unroll
     for (int p = 0; p < MeshT::NWV; ++p) {
         if (p >= M.nwv()) break;
@@ -602,16 +687,23 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         const uint32_t out = __ballot_sync(FULL, live && sd > TESS_TOL);  // vector3.rs:171
         M.inside.set_word(p, in);
         M.outside.set_word(p, out);
+        if ((out >> lane) & 1u) {  // list of the Outside vertices (for the sweep-free cut)
+            const uint32_t rk = n_out + __popc(out & ((1u << lane) - 1u));
+            if (rk < 32u) sm->ovl[rk] = (typename Cfg::Idx)v;
+        }
+        n_out += __popc(out);
         any_out |= out;
         any_incident |= lw & ~in & ~out;
         nlive += __popc(lw);
     }
+    M.n_outside = n_out;
     cnt_vc += nlive;
     if (!any_out) return 0;  // polyhedron.rs:408-410
 
     // ---- fast path: no vertex on the plane -> the whole cut in lane-parallel form ----------------
     if (!any_incident && !serial_only) {
-        const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv);
+        __syncwarp();
+        const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv, sweep_only);
         if (rc != CUT_FALLBACK) return rc;
     }
 
@@ -636,6 +728,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     }
 
     // ---- the walk (polyhedron.rs:475-623), warp-uniform ---------------------------------------
+    M.simple = false;  // vertices created here are not entered into vout[] (and may have valence > 3)
     const int cap_first = M.alloc_edge();
     const int cap_face = M.alloc_face();
     if (cap_first < 0 || cap_face < 0) return -1;
@@ -974,7 +1067,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     const Plane pl = {pq.x, pq.y, pq.z, pq.w};
                     const long long nid = sm->cand_id[l];
                     c_test += 1;
-                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u);
+                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u, (P.flags & 2u) != 0u);
                     if (rc < 0) {
                         if (rc == -1) status |= ST_CAPACITY_OVERFLOW;
                         failed = true;

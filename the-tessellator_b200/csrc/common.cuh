@@ -90,7 +90,7 @@ struct ClipParams {
     uint32_t* n_failed;            // [0] count of failed cells; [4] those that only exhausted the search table
     uint32_t failed_cap;
     uint32_t mark_large;           // OR ST_LARGE_PATH into the status of every row written
-    uint32_t flags;                // bit 0: serial walk only (TESS_FORCE_SERIAL=1, for A/B checks)
+    uint32_t flags;                // A/B checks: bit 0 serial walk only (TESS_FORCE_SERIAL=1), bit 1 always sweep the edge table (TESS_FORCE_SWEEP=1)
 };
 
 // radius / neighbour-cloud queries (query.cu)
