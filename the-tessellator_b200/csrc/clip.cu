@@ -350,116 +350,136 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
     const int lane = M.lane;
     const uint32_t lt = (1u << lane) - 1u;
 
-    // ---- 1. find the outgoing half-edges (one per crossed face) and what dies ---------------------
+    // ---- 1-3. the crossings: per crossed face the outgoing half-edge o (Inside -> Outside), the
+    //      re-entering half-edge r (pv Outside -> cv Inside), and the lanes ks / pk that hold the next /
+    //      previous crossing of the reference's walk --------------------------------------------------
     uint32_t K = 0;
     uint32_t deadbits = 0;              // sweep variant: bit p = my half-edge of pass p dies
     uint32_t keep_lo = 0, keep_hi = 0;  // sweep variant: faces my surviving half-edges belong to
     uint32_t my_dead = Cfg::NONE;       // adjacency variant: the dying half-edge this lane found
     uint32_t df_lo = 0, df_hi = 0;      //                    and the face it belongs to
     int n_pass = 0;
+    bool act = false;
+    uint32_t o = 0, f = 0, r = 0, pv = 0, cv = 0, fo = 0xFFFFu, ks = 0, pk = 0;
     bool adj = false;
     if constexpr (Cfg::REG) adj = M.simple && !sweep_only && 3u * M.n_outside <= 32u;
     if (adj) {
-        // 1a. every vertex is 3-valent and vout[] lists the half-edges leaving it: lane (i, j) takes
-        //     half-edge j of the i-th Outside vertex.  It either ends Outside too (it dies; so does its
-        //     flip, which the other vertex's lane finds) or ends Inside — then its flip is the outgoing
-        //     half-edge (Inside -> Outside) of a crossed face.
+        // Every vertex is 3-valent and vout[] lists the half-edges leaving it: lane (i, j) takes
+        // half-edge j of the i-th Outside vertex.  It either ends Outside too (it dies; so does its
+        // flip, which the other vertex's lane finds) or ends Inside — then it is the re-entering
+        // half-edge of its face, and its flip is the outgoing half-edge of the next crossed face.
         if constexpr (Cfg::REG) {
-            bool is_re = false;
-            uint32_t fl = 0;
+            uint32_t so = 0, fs = 0;
             if ((uint32_t)lane < 3u * M.n_outside) {
-                const uint32_t vi = (uint32_t)lane / 3u, j = (uint32_t)lane - 3u * vi;
-                const uint32_t e = sm->vout[3u * (uint32_t)sm->ovl[vi] + j];
+                const uint32_t vi = (uint32_t)lane / 3u;
+                pv = sm->ovl[vi];
+                const uint32_t e = sm->vout[3u * pv + ((uint32_t)lane - 3u * vi)];
                 const EW w = sm->edge[e];
-                fl = MeshT::e_flip(w);
-                if (M.outside.test(MeshT::e_tgt(w))) {
+                const uint32_t t = MeshT::e_tgt(w);
+                const uint32_t face = MeshT::e_face(w);
+                if (M.outside.test(t)) {
                     my_dead = e;
-                    const uint32_t face = MeshT::e_face(w);
                     if (face < 32u) df_lo = 1u << face; else df_hi = 1u << (face - 32u);
                 } else {
-                    is_re = true;
+                    act = true;
+                    r = e;
+                    cv = t;
+                    f = face;
+                    so = MeshT::e_flip(w);
+                    fs = MeshT::e_face(sm->edge[so]);
+                    sm->kof[f] = (uint8_t)lane;  // who holds the crossing of face f
                 }
             }
-            const uint32_t om = __ballot_sync(FULL, is_re);
-            if (is_re) {
-                const uint32_t k = __popc(om & lt);
-                sm->olist[k] = (Idx)fl;
-                sm->kof[fl] = (uint8_t)k;
-            }
-            K = __popc(om);
+            K = __popc(__ballot_sync(FULL, act));
+            if (K == 0u) return CUT_FALLBACK;  // SURVEY D17, reported by the serial path
+            __syncwarp();
+            // successor: the crossing of the face my re-entering half-edge's flip lies in
+            if (act) ks = sm->kof[fs] & 31u;
+            const bool s_act = __shfl_sync(FULL, act, (int)ks);
+            const uint32_t s_f = __shfl_sync(FULL, f, (int)ks);
+            const bool ok1 = !act || (s_act && s_f == fs);
+            if (act && ok1) sm->pred[ks] = (Idx)lane;
+            if (!__all_sync(FULL, ok1)) return CUT_FALLBACK;
+            __syncwarp();
+            // predecessor; succ is a bijection of the crossings iff every crossing is its predecessor's successor
+            if (act) pk = (uint32_t)sm->pred[lane] & 31u;
+            const bool p_act = __shfl_sync(FULL, act, (int)pk);
+            const uint32_t p_ks = __shfl_sync(FULL, ks, (int)pk);
+            o = __shfl_sync(FULL, so, (int)pk);
+            fo = __shfl_sync(FULL, r, (int)pk);
+            if (!act) fo = 0xFFFFu;
+            if (!__all_sync(FULL, !act || (p_act && p_ks == (uint32_t)lane))) return CUT_FALLBACK;
         }
     } else {
-    // 1b. sweep the half-edge table
-    n_pass = M.edge_passes();
-    if (n_pass > 32) return CUT_FALLBACK;  // deadbits holds one bit per pass
-    for (int p = 0; p < n_pass; ++p) {
-        const EW w = M.edge_of_pass(p);
-        bool is_out = false, dead = false, keep = false;
-        uint32_t face = 0;
-        if (!MeshT::e_is_free(w)) {
-            const uint32_t t = MeshT::e_tgt(w);
-            const uint32_t s = MeshT::e_tgt(sm->edge[MeshT::e_flip(w)]);
-            const bool tout = M.outside.test(t), sout = M.outside.test(s);
-            is_out = tout && !sout;  // source Inside (nothing is Incident)
-            dead = tout && sout;
-            keep = !dead;
-            face = MeshT::e_face(w);
-        }
-        const uint32_t om = __ballot_sync(FULL, is_out);
-        if (is_out) {
-            const uint32_t k = K + __popc(om & lt);
-            if (k < 32u) {
-                sm->olist[k] = (Idx)(32 * p + lane);
-                sm->kof[32 * p + lane] = (uint8_t)k;
+        // 1. sweep the half-edge table for the outgoing half-edges and for what dies
+        n_pass = M.edge_passes();
+        if (n_pass > 32) return CUT_FALLBACK;  // deadbits holds one bit per pass
+        for (int p = 0; p < n_pass; ++p) {
+            const EW w = M.edge_of_pass(p);
+            bool is_out = false, dead = false, keep = false;
+            uint32_t face = 0;
+            if (!MeshT::e_is_free(w)) {
+                const uint32_t t = MeshT::e_tgt(w);
+                const uint32_t s = MeshT::e_tgt(sm->edge[MeshT::e_flip(w)]);
+                const bool tout = M.outside.test(t), sout = M.outside.test(s);
+                is_out = tout && !sout;  // source Inside (nothing is Incident)
+                dead = tout && sout;
+                keep = !dead;
+                face = MeshT::e_face(w);
+            }
+            const uint32_t om = __ballot_sync(FULL, is_out);
+            if (is_out) {
+                const uint32_t k = K + __popc(om & lt);
+                if (k < 32u) {
+                    sm->olist[k] = (Idx)(32 * p + lane);
+                    sm->kof[32 * p + lane] = (uint8_t)k;
+                }
+            }
+            K += __popc(om);
+            deadbits |= (dead ? 1u : 0u) << p;
+            if (keep) {
+                if constexpr (Cfg::REG) {
+                    if (face < 32u) keep_lo |= 1u << face; else keep_hi |= 1u << (face - 32u);
+                } else {
+                    keep_lo = 1u;  // large cells: the face mask is rebuilt below, only if something died
+                }
             }
         }
-        K += __popc(om);
-        deadbits |= (dead ? 1u : 0u) << p;
-        if (keep) {
-            if constexpr (Cfg::REG) {
-                if (face < 32u) keep_lo |= 1u << face; else keep_hi |= 1u << (face - 32u);
-            } else {
-                keep_lo = 1u;  // large cells: the face mask is rebuilt below, only if something died
-            }
-        }
-    }
-    }
-    if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
-    __syncwarp();
-
-    // ---- 2. one lane per crossed face: find the re-entering half-edge ---------------------------
-    const bool act = (uint32_t)lane < K;
-    uint32_t o = 0, f = 0, r = 0, pv = 0, cv = 0, so = 0, fo = 0xFFFFu;
-    EW wo = 0;
-    bool ok = true;
-    if (act) {
-        o = sm->olist[lane];
-        wo = sm->edge[o];
-        f = MeshT::e_face(wo);
-        fo = MeshT::e_flip(wo);
-        pv = MeshT::e_tgt(wo);  // previous_vertex_index (:491), Outside
-        r = MeshT::e_next(wo);  // :506
-        EW wc = sm->edge[r];
-        cv = MeshT::e_tgt(wc);
-        int budget = Cfg::EMAX;
-        while (!M.inside.test(cv) && --budget > 0) {  // :529-544
-            pv = cv;
-            r = MeshT::e_next(wc);
-            wc = sm->edge[r];
+        if (K == 0u || K > 32u) return CUT_FALLBACK;  // K == 0: SURVEY D17, reported by the serial path
+        __syncwarp();
+        // 2. one lane per crossed face: walk from the outgoing to the re-entering half-edge
+        act = (uint32_t)lane < K;
+        uint32_t so = 0;
+        bool ok = true;
+        if (act) {
+            o = sm->olist[lane];
+            const EW wo = sm->edge[o];
+            f = MeshT::e_face(wo);
+            fo = MeshT::e_flip(wo);
+            pv = MeshT::e_tgt(wo);  // previous_vertex_index (:491), Outside
+            r = MeshT::e_next(wo);  // :506
+            EW wc = sm->edge[r];
             cv = MeshT::e_tgt(wc);
+            int budget = Cfg::EMAX;
+            while (!M.inside.test(cv) && --budget > 0) {  // :529-544
+                pv = cv;
+                r = MeshT::e_next(wc);
+                wc = sm->edge[r];
+                cv = MeshT::e_tgt(wc);
+            }
+            ok = budget > 0;
+            so = MeshT::e_flip(wc);  // the next crossed face's outgoing half-edge (:603-607)
         }
-        ok = budget > 0;
-        so = MeshT::e_flip(wc);  // the next crossed face's outgoing half-edge (:603-607)
+        // 3. cyclic order of the crossings (flip is a bijection, so succ is a permutation of them)
+        if (act) {
+            ks = sm->kof[so];
+            ok = ok && ks < K && sm->olist[ks] == (Idx)so;
+            if (ok) sm->pred[ks] = (Idx)lane;
+        }
+        if (!__all_sync(FULL, ok)) return CUT_FALLBACK;
+        __syncwarp();
+        if (act) pk = (uint32_t)sm->pred[lane];
     }
-    // ---- 3. cyclic order of the crossings ------------------------------------------------------
-    uint32_t ks = 0;
-    if (act) {
-        ks = sm->kof[so];
-        ok = ok && ks < K && sm->olist[ks] == (Idx)so;
-        if (ok) sm->pred[ks] = (Idx)lane;
-    }
-    if (!__all_sync(FULL, ok)) return CUT_FALLBACK;
-    __syncwarp();
     // the reference's first crossing: outgoing half-edge whose flip has the lowest slot (:413-432)
     const uint32_t k0 = __reduce_min_sync(FULL, (fo << 8) | (uint32_t)lane) & 0xFFu;
     // position of my crossing in the reference's walk order (k0 is 0): list ranking by pointer
@@ -476,15 +496,14 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
             d += d2;
             nxt = n2;
         }
-        // succ is a permutation of the crossings (flip is a bijection): everyone reaches k0 <=> one cycle
+        // succ is a permutation of the crossings: everyone reaches k0 <=> one cycle
         if (__any_sync(FULL, act && nxt != k0)) return CUT_FALLBACK;  // not a convex cut
         wi = ((uint32_t)lane == k0) ? 0u : K - d;
     }
     // ---- capacity: K vertices, 2K half-edges, one face ------------------------------------------
     {
-        int vfree_n = 0;
+        int vfree_n = 32 * (MeshT::NWV - M.nwv());
 #pragma unroll
-        vfree_n = 32 * (MeshT::NWV - M.nwv());
         for (int p = 0; p < MeshT::NWV; ++p) {
             if (p >= M.nwv()) break;
             vfree_n += 32 - __popc(M.vlive.word(p));
@@ -520,7 +539,6 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         ck = pop_slot(2 * (int)wi);
         br = pop_slot(2 * (int)wi + 1);
     }
-    const uint32_t pk = act ? (uint32_t)sm->pred[lane] : 0u;
     const uint32_t nv_pred = __shfl_sync(FULL, nv, (int)pk);  // previous_intersection (:550, :600)
     const uint32_t ck_pred = __shfl_sync(FULL, ck, (int)pk);
     const uint32_t ck0 = __shfl_sync(FULL, ck, (int)k0);
@@ -583,13 +601,17 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
             const uint32_t dm = __ballot_sync(FULL, my_dead != Cfg::NONE);
             if (dm) {
                 // Pool::remove in ascending slot order, as the sweep would do it
+                const uint32_t nd = __popc(dm);
+                if (my_dead != Cfg::NONE) sm->olist[__popc(dm & lt)] = (Idx)my_dead;
+                __syncwarp();
                 uint32_t rank = 0;
-                for (uint32_t m = dm; m; m &= m - 1u) rank += (__shfl_sync(FULL, my_dead, __ffs(m) - 1) < my_dead) ? 1u : 0u;
+#pragma unroll 4
+                for (uint32_t i = 0; i < nd; ++i) rank += ((uint32_t)sm->olist[i] < my_dead) ? 1u : 0u;
                 if (my_dead != Cfg::NONE) {
                     sm->estack[M.e_top + rank] = (Idx)my_dead;
                     sm->edge[my_dead] = MeshT::FREE_EDGE;
                 }
-                M.e_top += __popc(dm);
+                M.e_top += nd;
                 // faces of dying half-edges die unless the plane crosses them (then they hold an outgoing half-edge)
                 df_lo = __reduce_or_sync(FULL, df_lo);
                 df_hi = __reduce_or_sync(FULL, df_hi);
