@@ -166,6 +166,7 @@ struct WarpSmem {
     typename Cfg::Idx vfree[32];             // first free vertex slots
     uint8_t kof[Cfg::EMAX];                  // outgoing half-edge slot -> crossing index
     typename Cfg::Idx ovl[32];               // the (first 32) Outside vertices of the current plane
+    uint32_t dlist[8];                       // the dying half-edge slots of the current cut, one byte each
     // While every vertex is 3-valent (no plane has ever passed through a vertex of this cell) vout[3v..3v+2]
     // are the half-edges that start at vertex v: a cut is then found from its Outside vertices, without
     // sweeping the half-edge table.
@@ -602,11 +603,21 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
             if (dm) {
                 // Pool::remove in ascending slot order, as the sweep would do it
                 const uint32_t nd = __popc(dm);
-                if (my_dead != Cfg::NONE) sm->olist[__popc(dm & lt)] = (Idx)my_dead;
+                uint8_t* dl = reinterpret_cast<uint8_t*>(sm->dlist);
+                dl[lane] = 0xFFu;  // padding: no slot is below it
                 __syncwarp();
-                uint32_t rank = 0;
-#pragma unroll 4
-                for (uint32_t i = 0; i < nd; ++i) rank += ((uint32_t)sm->olist[i] < my_dead) ? 1u : 0u;
+                if (my_dead != Cfg::NONE) dl[__popc(dm & lt)] = (uint8_t)my_dead;
+                __syncwarp();
+                // rank = how many dying slots are below mine: four byte-compares per word
+                const uint32_t y4 = my_dead * 0x01010101u;
+                const uint32_t nw = (nd + 3u) >> 2;
+                uint32_t below = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < 8u; ++i) {
+                    if (i >= nw) break;
+                    below |= (__vcmpltu4(sm->dlist[i], y4) & 0x80808080u) >> i;
+                }
+                const uint32_t rank = __popc(below);
                 if (my_dead != Cfg::NONE) {
                     sm->estack[M.e_top + rank] = (Idx)my_dead;
                     sm->edge[my_dead] = MeshT::FREE_EDGE;
