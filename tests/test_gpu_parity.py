@@ -460,3 +460,58 @@ def test_awkward_inputs_match_oracle(tess, gen, ob, case):
     for k in ("tested", "cuts", "new_vertices", "faces", "degenerate_skips"):
         assert c[k] == r.counters[k], k
     d.close()
+
+
+# ------------------------------------------------------------------ streamed download --------
+def _host_arrays(n, cap):
+    return (np.full(n, -1.0), np.full(n + 1, 2**63, dtype=np.uint64), np.full(cap, -99, dtype=np.int64), np.full(cap, -1.0), np.full(n, 0xFFFFFFFF, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("chunks", [0, 3, 16])
+def test_streamed_host_results_equal_download(tess, gen, chunks):
+    """tess_compute_all_to_host: rows computed chunk by chunk, each chunk copied while the next is clipped —
+    the host arrays must equal tess_compute_all + download bit for bit (and the device batch too)."""
+    pts = gen.uniform(120_000, 71)
+    d = _diagram(tess, pts)
+    ref = d.compute_all_cells(outputs=ALL_OUT)
+    n, nf = ref.n_cells, ref.n_faces
+    vol, off, nbr, area, stat = _host_arrays(n, nf + 100)
+    b = d.compute_all_cells_to_host(vol, off, nbr, area, stat, n_chunks=chunks, outputs=ALL_OUT)
+    assert b.n_cells == n and b.n_faces == nf
+    assert np.array_equal(vol, ref.volumes) and np.array_equal(off.astype(np.int64), np.asarray(ref.face_offsets).astype(np.int64))
+    assert np.array_equal(nbr[:nf], ref.neighbors) and np.array_equal(area[:nf], ref.areas) and np.array_equal(stat, ref.status)
+    assert np.all(nbr[nf:] == -99) and np.all(area[nf:] == -1.0)  # nothing written past the faces
+    assert np.array_equal(b.volumes, ref.volumes) and np.array_equal(b.neighbors, ref.neighbors) and np.array_equal(b.areas, ref.areas)
+    d.close()
+
+
+def test_streamed_host_results_with_redo_cells(tess, gen):
+    """Cells that need a redo pass (voids: table exhausted; a 300-neighbour cell: large path) appear after
+    chunks were already copied: the call must repack and copy everything again."""
+    u = gen.uniform(300, 54)
+    th, ph = np.arccos(2 * u[:, 0] - 1), 2 * np.pi * u[:, 1]
+    shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
+    bg = gen.uniform(60_000, 55)
+    pts = np.concatenate([[[0.5, 0.5, 0.5]], shell, bg[np.linalg.norm(bg - 0.5, axis=1) > 0.35]])
+    d = _diagram(tess, pts)
+    ref = d.compute_all_cells(outputs=ALL_OUT)
+    n, nf = ref.n_cells, ref.n_faces
+    vol, off, nbr, area, stat = _host_arrays(n, nf)
+    d.compute_all_cells_to_host(vol, off, nbr, area, stat, n_chunks=8, outputs=ALL_OUT)
+    assert np.array_equal(vol, ref.volumes) and np.array_equal(off.astype(np.int64), np.asarray(ref.face_offsets).astype(np.int64))
+    assert np.array_equal(nbr, ref.neighbors) and np.array_equal(area, ref.areas) and np.array_equal(stat, ref.status)
+    assert abs(vol.sum() - 1.0) <= 1e-12
+    d.close()
+
+
+def test_streamed_host_capacity_error_and_optional_arrays(tess, gen):
+    pts = gen.uniform(40_000, 72)
+    d = _diagram(tess, pts)
+    ref = d.compute_all_cells(outputs=ALL_OUT)
+    vol, off, nbr, area, stat = _host_arrays(ref.n_cells, ref.n_faces // 2)
+    with pytest.raises(tess.TessError):
+        d.compute_all_cells_to_host(vol, off, nbr, area, stat, n_chunks=4, outputs=ALL_OUT)
+    vol, off, nbr, area, stat = _host_arrays(ref.n_cells, ref.n_faces)
+    d.compute_all_cells_to_host(vol, None, nbr, None, None, n_chunks=4, outputs=1 | 2)  # volumes + neighbours only
+    assert np.array_equal(vol, ref.volumes) and np.array_equal(nbr, ref.neighbors) and np.all(area == -1.0)
+    d.close()

@@ -26,7 +26,7 @@ SYMBOLS = (
     "tess_last_error", "tess_version", "tess_device_count", "tess_opts_default",
     "tess_diagram_create", "tess_diagram_destroy", "tess_diagram_add_particles", "tess_diagram_add_particles_device",
     "tess_diagram_clear", "tess_diagram_initialize", "tess_diagram_initialize_slab", "tess_diagram_grid_info",
-    "tess_diagram_copy_grid", "tess_diagram_copy_search_order", "tess_compute_all", "tess_compute_at_points",
+    "tess_diagram_copy_grid", "tess_diagram_copy_search_order", "tess_compute_all", "tess_compute_all_to_host", "tess_compute_at_points",
     "tess_result_free", "tess_result_n_cells", "tess_result_volumes", "tess_result_face_offsets", "tess_result_neighbors",
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
     "tess_result_face_vertex_offsets", "tess_result_face_vertex_indices",
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     sig("tess_diagram_copy_grid", ci, vp, vp, vp, vp)
     sig("tess_diagram_copy_search_order", ci, vp, C.c_int32, P(u64), vp, vp, P(ci))
     sig("tess_compute_all", ci, vp, P(Opts), P(vp))
+    sig("tess_compute_all_to_host", ci, vp, P(Opts), ci, vp, vp, vp, vp, vp, C.c_uint64, P(vp))
     sig("tess_compute_at_points", ci, vp, vp, sz, P(Opts), P(vp))
     sig("tess_result_free", None, vp)
     sig("tess_result_n_cells", ci, vp, P(u64), P(u64))

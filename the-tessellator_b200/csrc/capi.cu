@@ -571,7 +571,18 @@ struct Scratch {  // stream-ordered temporaries
     }
 };
 
-int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* query_host, size_t n_query, tess_result** out) {
+// Host buffers tess_compute_all_to_host streams the results into, chunk of rows by chunk of rows.
+struct HostSink {
+    double* volumes;
+    uint64_t* face_offsets;
+    int64_t* neighbors;
+    double* areas;
+    uint32_t* status;
+    uint64_t face_capacity;
+    int n_chunks;
+};
+
+int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* query_host, size_t n_query, tess_result** out, const HostSink* sink = nullptr) {
     tess_opts o;
     if (opts_in) o = *opts_in; else tess_opts_default(&o);
     cudaStream_t s = static_cast<cudaStream_t>(o.stream);
@@ -671,75 +682,124 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
     P.flags = (std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u) | (std::getenv("TESS_FORCE_SWEEP") ? 2u : 0u);
-    cudaEvent_t ev[5];
-    for (auto& e : ev) TESS_CUDA_CHECK(cudaEventCreate(&e));
-    struct EvGuard {
-        cudaEvent_t* e;
-        ~EvGuard() { for (int i = 0; i < 5; ++i) cudaEventDestroy(e[i]); }
-    } ev_guard{ev};
-    TESS_CUDA_CHECK(cudaEventRecord(ev[0], s));
-    launch_clip(P, /*large=*/false, s);
-    TESS_CUDA_CHECK(cudaEventRecord(ev[1], s));
+    // ---- the pipeline ------------------------------------------------------------------------------
+    // The rows are computed in C chunks (C = 1 unless the results stream to host buffers,
+    // tess_compute_all_to_host).  Per chunk: clip its cells in sorted (spatial) order; redo what the
+    // small tables / the default shell table could not finish; extend the CSR offsets; pack the
+    // chunk's rows; and, when streaming, copy them to the host on a second stream.  The clip launch
+    // of chunk c+1 is enqueued before chunk c is finished off, so the device never waits for the
+    // host, and the copy of chunk c overlaps the clip kernel of chunk c+2.
+    const bool streaming = sink && !query && !want_vtx && !d->slab && sink->n_chunks > 1 && n_rows >= (size_t)sink->n_chunks * 1024u;
+    const int C = streaming ? sink->n_chunks : 1;
+    const uint64_t face_cap = sink ? sink->face_capacity : 0;
+    auto row_begin = [&](int c) { return (size_t)((unsigned long long)n_rows * (unsigned long long)c / (unsigned long long)C); };
 
-    // CSR offsets; one sync fetches {n_failed, total}
-    launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
-    uint32_t n_failed = 0, n_table_only = 0;
-    uint64_t total = 0;
-    TESS_CUDA_CHECK(cudaMemcpyAsync(&n_failed, ctrl + 1, sizeof(n_failed), cudaMemcpyDeviceToHost, s));
-    TESS_CUDA_CHECK(cudaMemcpyAsync(&n_table_only, ctrl + 5, sizeof(n_table_only), cudaMemcpyDeviceToHost, s));
-    TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
-    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-    tr.mark("clip + scan");
+    struct Events {
+        std::vector<cudaEvent_t> ev;
+        cudaStream_t copy_stream = nullptr;
+        uint64_t* pinned = nullptr;
+        ~Events() {
+            for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            if (copy_stream) cudaStreamDestroy(copy_stream);
+        }
+    } E;
+    E.ev.resize(3 * (size_t)C + 2);  // per chunk: clip begin, clip end, packed; + whole-call begin / end
+    for (auto& e : E.ev) TESS_CUDA_CHECK(cudaEventCreate(&e));
+    cudaEvent_t ev_begin = E.ev[3 * (size_t)C], ev_end = E.ev[3 * (size_t)C + 1];
+    // page-locked words the per-chunk counts land in: allocated once per host thread (cudaFreeHost
+    // synchronises the device, so it is kept out of the per-call path)
+    struct PinnedWords {
+        uint64_t* p = nullptr;
+        ~PinnedWords() { if (p) cudaFreeHost(p); }
+    };
+    static thread_local PinnedWords pinned_words;
+    constexpr size_t kPinnedWords = 4 * 256;  // n_chunks <= 256
+    if (!pinned_words.p) TESS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_words.p), sizeof(uint64_t) * kPinnedWords));
+    E.pinned = pinned_words.p;
+    std::memset(E.pinned, 0, sizeof(uint64_t) * 4 * (size_t)C);
+    uint32_t *work_list = nullptr, *flags = nullptr;
+    uint64_t* pos = nullptr;
+    if (streaming) {
+        TESS_CUDA_CHECK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
+        work_list = tmp.get<uint32_t>(n_rows);
+        flags = tmp.get<uint32_t>(n_rows + 1);
+        pos = tmp.get<uint64_t>(n_rows + 1);
+        r->nbr = dmalloc<int64_t>(face_cap, s);  // the caller's capacity: the total is not known before the last chunk
+        if (want_area) r->area = dmalloc<double>(face_cap, s);
+    }
+    TESS_CUDA_CHECK(cudaEventRecord(ev_begin, s));
 
-    // ---- redo passes: cells the small tables / the default shell table could not finish -----------
+    auto enqueue_clip = [&](int c) {
+        const size_t r0 = row_begin(c), r1 = row_begin(c + 1);
+        ClipParams Q = P;
+        if (C > 1) {  // the chunk's cells in ascending slot order
+            launch_chunk_flags(P.row_of_slot, d->own_slot_begin, n_rows, (uint32_t)r0, (uint32_t)r1, flags, s);
+            launch_exclusive_scan_u32_to_u64(flags, pos, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
+            launch_chunk_scatter(flags, pos, d->own_slot_begin, n_rows, work_list + r0, s);
+            Q.n_work = (uint32_t)(r1 - r0);
+            Q.work_slots = work_list + r0;
+        }
+        TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c], s));
+        launch_clip(Q, /*large=*/false, s);
+        TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c + 1], s));
+        // failures so far: [0] all, [1] those that only ran out of search table
+        TESS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(E.pinned + 4 * c), ctrl + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(E.pinned + 4 * c + 1), ctrl + 5, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c + 2], s));
+    };
+
+    // ---- redo passes for `count` failed cells (sorted slots at failed_list):
     //   A: the same small-cell kernel with a wider search table (cells in voids only ran out of table);
     //   B: what still fails (more than 64 vertices / 40 faces) goes to the large-cell configuration,
     //      with tables of doubled radius until every walk terminates.
-    uint32_t n_redo = 0, n_redo_b = 0;
-    int64_t *sa_nbr = nullptr, *lg_nbr = nullptr;
-    double *sa_area = nullptr, *lg_area = nullptr;
-    uint16_t *sa_flen = nullptr, *lg_flen = nullptr;
-    uint32_t* failed_b = nullptr;
+    struct Redo {
+        uint32_t n_a = 0, n_b = 0;
+        const uint32_t *list_a = nullptr, *list_b = nullptr;
+        int64_t *sa_nbr = nullptr, *lg_nbr = nullptr;
+        double *sa_area = nullptr, *lg_area = nullptr;
+        uint16_t *sa_flen = nullptr, *lg_flen = nullptr;
+    };
     const uint32_t lstride = clip_large_fmax();
-    if (n_failed > 0) {
-        n_redo = n_failed;
+    uint32_t total_redo_a = 0, total_redo_b = 0;
+    int final_R = 0;
+    auto redo = [&](uint32_t* failed_list, uint32_t count, uint32_t table_only, Redo& ro) -> int {
         const int cpd_m1 = std::max(static_cast<int>(d->grid.cpd) - 1, 1);
         int R = std::min(std::max(3 * R0, 24), cpd_m1);
-        const bool pass_a = n_table_only > 0;
-        if (!pass_a) {  // every failure is a table overflow of the small configuration: straight to pass B
-            failed_b = failed;
-            n_redo_b = n_redo;
-            n_redo = 0;
+        uint32_t* list_b = nullptr;
+        if (table_only == 0) {  // every failure is a table overflow of the small configuration: straight to pass B
+            list_b = failed_list;
+            ro.n_b = count;
         } else {
-        sa_nbr = tmp.get<int64_t>((size_t)n_redo * fstride);
-        sa_area = want_area ? tmp.get<double>((size_t)n_redo * fstride) : nullptr;
-        sa_flen = want_vtx ? tmp.get<uint16_t>((size_t)n_redo * fstride) : nullptr;
-        failed_b = tmp.get<uint32_t>(n_redo);
-        {
+            ro.n_a = count;
+            ro.list_a = failed_list;
+            ro.sa_nbr = tmp.get<int64_t>((size_t)count * fstride);
+            ro.sa_area = want_area ? tmp.get<double>((size_t)count * fstride) : nullptr;
+            ro.sa_flen = want_vtx ? tmp.get<uint16_t>((size_t)count * fstride) : nullptr;
+            list_b = tmp.get<uint32_t>(count);
             const ShellTable& t2 = d->table(R, s);
             ClipParams Q = P;
             Q.table = t2.dev.as<ShellEntry>();
             Q.table_len = t2.len;
             Q.table_full = t2.full ? 1u : 0u;
-            Q.n_work = n_redo;
-            Q.work_slots = failed;
-            Q.st_nbr = sa_nbr; Q.st_area = sa_area; Q.st_flen = sa_flen; Q.fstride = fstride; Q.stage_by_work = 1;
-            Q.failed_slots = failed_b;
+            Q.n_work = count;
+            Q.work_slots = failed_list;
+            Q.st_nbr = ro.sa_nbr; Q.st_area = ro.sa_area; Q.st_flen = ro.sa_flen; Q.fstride = fstride; Q.stage_by_work = 1;
+            Q.failed_slots = list_b;
             Q.n_failed = ctrl + 2;
-            Q.failed_cap = n_redo;
+            Q.failed_cap = count;
             Q.mark_large = 1;
             TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 2, 0, sizeof(uint32_t), s));
             launch_clip(Q, /*large=*/false, s);
-            TESS_CUDA_CHECK(cudaMemcpyAsync(&n_redo_b, ctrl + 2, sizeof(n_redo_b), cudaMemcpyDeviceToHost, s));
+            TESS_CUDA_CHECK(cudaMemcpyAsync(&ro.n_b, ctrl + 2, sizeof(ro.n_b), cudaMemcpyDeviceToHost, s));
             TESS_CUDA_CHECK(cudaStreamSynchronize(s));
         }
-        }
-        if (n_redo_b > 0) {
-            if (n_redo_b > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
-            lg_nbr = tmp.get<int64_t>((size_t)n_redo_b * lstride);
-            lg_area = want_area ? tmp.get<double>((size_t)n_redo_b * lstride) : nullptr;
-            lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)n_redo_b * lstride) : nullptr;
-            uint32_t* failed_c = tmp.get<uint32_t>(n_redo_b);
+        ro.list_b = list_b;
+        if (ro.n_b > 0) {
+            if (ro.n_b > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
+            ro.lg_nbr = tmp.get<int64_t>((size_t)ro.n_b * lstride);
+            ro.lg_area = want_area ? tmp.get<double>((size_t)ro.n_b * lstride) : nullptr;
+            ro.lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)ro.n_b * lstride) : nullptr;
+            uint32_t* failed_c = tmp.get<uint32_t>(ro.n_b);
             unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
             for (int attempt = 0; attempt < 12; ++attempt) {
                 const ShellTable& t2 = d->table(R, s);
@@ -747,14 +807,14 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
                 Q.table = t2.dev.as<ShellEntry>();
                 Q.table_len = t2.len;
                 Q.table_full = t2.full ? 1u : 0u;
-                Q.n_work = n_redo_b;
-                Q.work_slots = failed_b;
-                Q.st_nbr = lg_nbr; Q.st_area = lg_area; Q.st_flen = lg_flen; Q.fstride = lstride; Q.stage_by_work = 1;
+                Q.n_work = ro.n_b;
+                Q.work_slots = list_b;
+                Q.st_nbr = ro.lg_nbr; Q.st_area = ro.lg_area; Q.st_flen = ro.lg_flen; Q.fstride = lstride; Q.stage_by_work = 1;
                 Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
                 if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
                 Q.failed_slots = failed_c;
                 Q.n_failed = ctrl + 3;
-                Q.failed_cap = n_redo_b;
+                Q.failed_cap = ro.n_b;
                 Q.mark_large = 1;
                 TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 3, 0, sizeof(uint32_t), s));
                 launch_clip(Q, /*large=*/true, s);
@@ -768,27 +828,90 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
                 unsigned long long h[CNT_N];
                 TESS_CUDA_CHECK(cudaMemcpyAsync(h, redo_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
                 TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-                for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] = h[i];
+                for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] += h[i];
             }
         }
-        launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
-        TESS_CUDA_CHECK(cudaMemcpyAsync(&total, r->offsets + n_rows, sizeof(total), cudaMemcpyDeviceToHost, s));
-        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (std::getenv("TESS_TRACE")) std::fprintf(stderr, "[tess trace] redo: %u cells failed the first pass (%u for lack of table only); pass A re-ran %u, pass B (large cells, final R=%d) %u\n", n_failed, n_table_only, n_redo, R, n_redo_b);
-    }
+        total_redo_a += ro.n_a;
+        total_redo_b += ro.n_b;
+        final_R = std::max(final_R, R);
+        return TESS_OK;
+    };
 
-    tr.mark("redo");
-    TESS_CUDA_CHECK(cudaEventRecord(ev[2], s));
+    uint32_t fail_prev = 0, table_only_prev = 0;
+    uint64_t total = 0, copied = 0;
+    uint32_t* flen_csr = nullptr;
+    double ms_clip = 0.0;
+    auto finish = [&](int c) -> int {
+        const size_t r0 = row_begin(c), r1 = row_begin(c + 1);
+        TESS_CUDA_CHECK(cudaEventSynchronize(E.ev[3 * c + 2]));
+        {
+            float t = 0;
+            cudaEventElapsedTime(&t, E.ev[3 * c], E.ev[3 * c + 1]);
+            ms_clip += t;
+        }
+        const uint32_t fail_now = *reinterpret_cast<uint32_t*>(E.pinned + 4 * c), table_only_now = *reinterpret_cast<uint32_t*>(E.pinned + 4 * c + 1);
+        Redo ro;
+        if (fail_now > fail_prev) {
+            const int rc = redo(failed + fail_prev, fail_now - fail_prev, table_only_now - table_only_prev, ro);
+            if (rc != TESS_OK) return rc;
+        }
+        fail_prev = fail_now;
+        table_only_prev = table_only_now;
+        // CSR offsets: an exclusive scan only looks back, so the scan of the whole array is final up to r1
+        // (rows of the next chunk may already hold their counts)
+        launch_exclusive_scan_u32_to_u64(r->nfaces, r->offsets, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(E.pinned + 4 * c + 2, r->offsets + r1, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        total = E.pinned[4 * c + 2];
+        if (sink && total > face_cap) return fail(TESS_ERR_CAPACITY, "tess_compute_all_to_host: the cells have more faces than face_capacity");
+        if (!streaming) {
+            r->nbr = dmalloc<int64_t>(total, s);
+            if (want_area) r->area = dmalloc<double>(total, s);
+            flen_csr = want_vtx ? tmp.get<uint32_t>(total + 1) : nullptr;
+            if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(flen_csr + total, 0, sizeof(uint32_t), s));
+        }
+        launch_compact_faces(r->status + r0, r->offsets + r0, st_nbr + r0 * fstride, st_area ? st_area + r0 * fstride : nullptr, st_flen ? st_flen + r0 * fstride : nullptr,
+                             fstride, r1 - r0, r->nbr, r->area, flen_csr, s);
+        if (ro.n_a)  // pass A rows (rows redone again by pass B are overwritten right after)
+            launch_compact_redo(ro.list_a, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.sa_nbr, ro.sa_area, ro.sa_flen, fstride, ro.n_a, r->nbr, r->area, flen_csr, s);
+        if (ro.n_b)
+            launch_compact_redo(ro.list_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.lg_nbr, ro.lg_area, ro.lg_flen, lstride, ro.n_b, r->nbr, r->area, flen_csr, s);
+        launch_clear_status_bits(r->status + r0, r1 - r0, ST_LARGE_PATH, s);  // internal marker of the redo passes
+        if (streaming) {
+            // the packed chunk goes to the host while the next chunks are clipped
+            cudaEvent_t packed = E.ev[3 * c];  // (its first use, the clip-begin time stamp, has been read)
+            TESS_CUDA_CHECK(cudaEventRecord(packed, s));
+            TESS_CUDA_CHECK(cudaStreamWaitEvent(E.copy_stream, packed, 0));
+            cudaStream_t cs = E.copy_stream;
+            if (sink->volumes) TESS_CUDA_CHECK(cudaMemcpyAsync(sink->volumes + r0, r->vol + r0, sizeof(double) * (r1 - r0), cudaMemcpyDeviceToHost, cs));
+            if (sink->status) TESS_CUDA_CHECK(cudaMemcpyAsync(sink->status + r0, r->status + r0, sizeof(uint32_t) * (r1 - r0), cudaMemcpyDeviceToHost, cs));
+            if (sink->face_offsets)
+                TESS_CUDA_CHECK(cudaMemcpyAsync(sink->face_offsets + r0, r->offsets + r0, sizeof(uint64_t) * (r1 - r0 + (c == C - 1 ? 1 : 0)), cudaMemcpyDeviceToHost, cs));
+            if (sink->neighbors && total > copied)
+                TESS_CUDA_CHECK(cudaMemcpyAsync(sink->neighbors + copied, r->nbr + copied, sizeof(int64_t) * (total - copied), cudaMemcpyDeviceToHost, cs));
+            if (sink->areas && want_area && total > copied)
+                TESS_CUDA_CHECK(cudaMemcpyAsync(sink->areas + copied, r->area + copied, sizeof(double) * (total - copied), cudaMemcpyDeviceToHost, cs));
+            copied = total;
+        }
+        return TESS_OK;
+    };
+
+    for (int c = 0; c < C; ++c) {
+        enqueue_clip(c);
+        if (c > 0) {
+            const int rc = finish(c - 1);
+            if (rc != TESS_OK) return rc;
+        }
+    }
+    {
+        const int rc = finish(C - 1);
+        if (rc != TESS_OK) return rc;
+    }
     r->n_faces = total;
-    r->nbr = dmalloc<int64_t>(total, s);
-    if (want_area) r->area = dmalloc<double>(total, s);
-    uint32_t* flen_csr = want_vtx ? tmp.get<uint32_t>(total + 1) : nullptr;
-    if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(flen_csr + total, 0, sizeof(uint32_t), s));
-    launch_compact_faces(r->status, r->offsets, st_nbr, st_area, st_flen, fstride, n_rows, r->nbr, r->area, flen_csr, s);
-    if (n_redo)  // pass A rows (rows redone again by pass B are overwritten right after)
-        launch_compact_redo(failed, P.row_of_slot, P.row_base, r->nfaces, r->offsets, sa_nbr, sa_area, sa_flen, fstride, n_redo, r->nbr, r->area, flen_csr, s);
-    if (n_redo_b)
-        launch_compact_redo(failed_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, lg_nbr, lg_area, lg_flen, lstride, n_redo_b, r->nbr, r->area, flen_csr, s);
+    if (std::getenv("TESS_TRACE") && (total_redo_a || total_redo_b))
+        std::fprintf(stderr, "[tess trace] redo: pass A (wider table) re-ran %u cells, pass B (large cells, final R=%d) %u\n", total_redo_a, final_R, total_redo_b);
+    tr.mark("clip + redo + pack");
+
     if (want_vtx) {
         unsigned long long used[2] = {0, 0};
         TESS_CUDA_CHECK(cudaMemcpyAsync(used, g_cursor, sizeof(used), cudaMemcpyDeviceToHost, s));
@@ -809,19 +932,20 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         launch_gather_vertices(r->nverts, vbase, r->voffsets, gv_xyz, n_rows, r->vtx, s);
         launch_gather_loops(nloops, lbase, r->offsets, r->fv_offsets, gl_idx, n_rows, r->fv_idx, s);
     }
-    TESS_CUDA_CHECK(cudaEventRecord(ev[3], s));
+    if (sink && !streaming) {  // slab diagrams and small inputs: one copy of the finished arrays
+        const int rc = tess_result_download(r.get(), sink->volumes, sink->face_offsets, sink->neighbors, want_area ? sink->areas : nullptr, sink->status, s);
+        if (rc != TESS_OK) return rc;
+    }
+    TESS_CUDA_CHECK(cudaEventRecord(ev_end, s));
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-    tr.mark("alloc out + compaction");
+    if (streaming) TESS_CUDA_CHECK(cudaStreamSynchronize(E.copy_stream));
+    tr.mark("outputs");
     {
-        float a = 0, b = 0, c = 0, t = 0;
-        cudaEventElapsedTime(&a, ev[0], ev[1]);
-        cudaEventElapsedTime(&b, ev[1], ev[2]);
-        cudaEventElapsedTime(&c, ev[2], ev[3]);
-        cudaEventElapsedTime(&t, ev[0], ev[3]);
-        r->ms_clip = a;
-        const bool redone = n_redo || n_redo_b;
-        r->ms_redo = redone ? b : 0.0;  // includes the (small) scans before/after the redo passes
-        r->ms_outputs = c + (redone ? 0.0 : b);
+        float t = 0;
+        cudaEventElapsedTime(&t, ev_begin, ev_end);
+        r->ms_clip = ms_clip;
+        r->ms_redo = 0.0;  // folded into the rest: redo passes, scans, packing (and, when streaming, waiting for copies)
+        r->ms_outputs = std::max(0.0, (double)t - ms_clip);
         r->ms_total = t;
     }
     *out = r.release();
@@ -838,6 +962,19 @@ int tess_compute_all(const tess_diagram* d, const tess_opts* opts, tess_result**
     if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
     TESS_TRY
     return compute_impl(d, opts, nullptr, 0, out);
+    TESS_CATCH
+}
+
+int tess_compute_all_to_host(const tess_diagram* d, const tess_opts* opts, int n_chunks, double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas,
+                             uint32_t* status, uint64_t face_capacity, tess_result** out) {
+    if (!d || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (opts && (opts->outputs & TESS_OUT_VERTICES)) return fail(TESS_ERR_INVALID, "tess_compute_all_to_host does not stream vertex geometry; use tess_compute_all");
+    if (n_chunks < 0 || n_chunks > 256) return fail(TESS_ERR_INVALID, "n_chunks must be in [0, 256]");
+    TESS_TRY
+    HostSink sink{volumes, face_offsets, neighbors, areas, status, face_capacity, n_chunks == 0 ? 8 : n_chunks};
+    return compute_impl(d, opts, nullptr, 0, out, &sink);
     TESS_CATCH
 }
 

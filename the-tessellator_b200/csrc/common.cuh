@@ -141,7 +141,11 @@ uint32_t clip_large_fmax();
 uint32_t clip_large_vmax();
 
 void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t n, void* tmp, size_t tmp_bytes, cudaStream_t s);
-void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s);
+void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s, uint64_t face_cap = ~0ull);
+void launch_clear_status_bits(uint32_t* status, size_t n, uint32_t bits, cudaStream_t s);
+// streaming: work list (ascending sorted slots) of the rows [row_lo, row_hi)
+void launch_chunk_flags(const uint32_t* row_of_slot, uint32_t slot_begin, size_t n, uint32_t row_lo, uint32_t row_hi, uint32_t* flags, cudaStream_t s);
+void launch_chunk_scatter(const uint32_t* flags, const uint64_t* pos, uint32_t slot_begin, size_t n, uint32_t* work_slots, cudaStream_t s);
 void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot, uint32_t row_base, const uint32_t* nfaces, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride, size_t n_work, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s);
 void launch_gather_vertices(const uint32_t* nverts, const unsigned long long* vbase, const uint64_t* voffsets, const double* pool, size_t n_rows, double* vtx, cudaStream_t s);
 void launch_gather_loops(const uint32_t* nloops, const unsigned long long* lbase, const uint64_t* face_offsets, const uint64_t* fv_offsets, const uint32_t* pool, size_t n_rows, uint32_t* out, cudaStream_t s);

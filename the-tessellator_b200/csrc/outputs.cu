@@ -18,13 +18,13 @@ constexpr int kRowsPerBlock = 256;
 __global__ void __launch_bounds__(256) compact_faces_kernel(const uint32_t* __restrict__ status, const uint64_t* __restrict__ offsets,
                                                             const int64_t* __restrict__ st_nbr, const double* __restrict__ st_area,
                                                             const uint16_t* __restrict__ st_flen, uint32_t fstride, size_t n_rows,
-                                                            int64_t* __restrict__ nbr, double* __restrict__ area, uint32_t* __restrict__ flen) {
+                                                            int64_t* __restrict__ nbr, double* __restrict__ area, uint32_t* __restrict__ flen, uint64_t face_cap) {
     __shared__ uint64_t s_off[kRowsPerBlock + 1];
     const size_t row0 = (size_t)blockIdx.x * kRowsPerBlock;
     const int rows = (int)min((size_t)kRowsPerBlock, n_rows - row0);
     for (int i = threadIdx.x; i <= rows; i += blockDim.x) s_off[i] = offsets[row0 + i];
     __syncthreads();
-    const uint64_t begin = s_off[0], end = s_off[rows];
+    const uint64_t begin = s_off[0], end = min(s_off[rows], face_cap);  // never past the arrays' capacity (the host reports the overflow)
     for (uint64_t p = begin + threadIdx.x; p < end; p += blockDim.x) {
         int lo = 0, hi = rows;  // largest r with s_off[r] <= p
         while (hi - lo > 1) {
@@ -100,6 +100,30 @@ __global__ void __launch_bounds__(256) volume_partial_kernel(const double* __res
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
 }
+// Streaming (tess_compute_all_to_host): the sorted slots whose output row lies in [row_lo, row_hi), in
+// ascending slot order — the work list of one chunk of rows.  flags -> exclusive scan -> scatter.
+__global__ void __launch_bounds__(256) chunk_flags_kernel(const uint32_t* __restrict__ row_of_slot, uint32_t slot_begin, size_t n, uint32_t row_lo, uint32_t row_hi,
+                                                          uint32_t* __restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) {
+        const uint32_t row = row_of_slot[slot_begin + i];
+        f = (row >= row_lo && row < row_hi) ? 1u : 0u;
+    }
+    flags[i] = f;  // flags[n] = 0 closes the scan
+}
+__global__ void __launch_bounds__(256) chunk_scatter_kernel(const uint32_t* __restrict__ flags, const uint64_t* __restrict__ pos, uint32_t slot_begin, size_t n,
+                                                            uint32_t* __restrict__ work_slots) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) work_slots[pos[i]] = slot_begin + (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) clear_status_bits_kernel(uint32_t* __restrict__ status, size_t n, uint32_t bits) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) status[i] &= ~bits;
+}
+
 __global__ void volume_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double acc = 0.0;
@@ -111,10 +135,32 @@ __global__ void volume_final_kernel(const double* __restrict__ partial, int nb, 
 }  // namespace
 
 void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const int64_t* st_nbr, const double* st_area, const uint16_t* st_flen, uint32_t fstride,
-                          size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s) {
+                          size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s, uint64_t face_cap) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
-    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, st_flen, fstride, n_rows, nbr, area, flen);
+    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, st_flen, fstride, n_rows, nbr, area, flen, face_cap);
+    note_launch();
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_clear_status_bits(uint32_t* status, size_t n, uint32_t bits, cudaStream_t s) {
+    if (!n) return;
+    clear_status_bits_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(status, n, bits);
+    note_launch();
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_chunk_flags(const uint32_t* row_of_slot, uint32_t slot_begin, size_t n, uint32_t row_lo, uint32_t row_hi, uint32_t* flags, cudaStream_t s) {
+    const unsigned int nb = (unsigned int)((n + 1 + 255) / 256);
+    chunk_flags_kernel<<<nb, 256, 0, s>>>(row_of_slot, slot_begin, n, row_lo, row_hi, flags);
+    note_launch();
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_chunk_scatter(const uint32_t* flags, const uint64_t* pos, uint32_t slot_begin, size_t n, uint32_t* work_slots, cudaStream_t s) {
+    if (!n) return;
+    const unsigned int nb = (unsigned int)((n + 255) / 256);
+    chunk_scatter_kernel<<<nb, 256, 0, s>>>(flags, pos, slot_begin, n, work_slots);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }

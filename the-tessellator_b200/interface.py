@@ -314,6 +314,38 @@ class Diagram:
         check(_lib.lib().tess_compute_all(self._h, C.byref(o), C.byref(h)))
         return CellBatch(h.value, self.device)
 
+    def compute_all_cells_to_host(self, volumes, face_offsets, neighbors, areas, status, n_chunks: int = 0, search_radius: Optional[float] = None,
+                                  target_group: Optional[int] = None, outputs: Optional[int] = None, table_radius: int = 0, stream: int = 0) -> CellBatch:
+        """compute_all_cells with the results streamed into caller-owned host arrays while later cells are
+        still being computed (tess_compute_all_to_host).  Each argument is a C-contiguous host array of the
+        right dtype — numpy, or anything with `data_ptr()` / `numel()` such as a pinned torch tensor — or None:
+        volumes f64[n], face_offsets u64/i64[n+1], neighbors i64[cap], areas f64[cap], status u32/i32[n]; the
+        capacity in faces is the smaller of len(neighbors) and len(areas).  Page-locked arrays overlap the copy
+        with the compute.  Returns the device-side batch; the host arrays are complete on return."""
+        def ptr_len(a, itemsize):
+            if a is None:
+                return None, None
+            if hasattr(a, "data_ptr"):
+                assert a.is_contiguous() and a.element_size() == itemsize
+                return a.data_ptr(), a.numel()
+            assert a.flags["C_CONTIGUOUS"] and a.itemsize == itemsize
+            return a.ctypes.data, a.size
+        pv, nv = ptr_len(volumes, 8)
+        po, no = ptr_len(face_offsets, 8)
+        pn, nn = ptr_len(neighbors, 8)
+        pa, na = ptr_len(areas, 8)
+        ps, ns = ptr_len(status, 4)
+        n = self._n
+        if (nv is not None and nv < n) or (no is not None and no < n + 1) or (ns is not None and ns < n):
+            raise ValueError("compute_all_cells_to_host: per-cell arrays are too short")
+        caps = [c for c in (nn, na) if c is not None]
+        o = self._opts(search_radius, target_group, outputs, table_radius, stream)
+        if pa is not None and not (o.outputs & _lib.OUT_AREAS):
+            pa = None
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_compute_all_to_host(self._h, C.byref(o), int(n_chunks), pv, po, pn, pa, ps, min(caps) if caps else 0, C.byref(h)))
+        return CellBatch(h.value, self.device)
+
     def compute_cells_at(self, points: np.ndarray, search_radius: Optional[float] = None, target_group: Optional[int] = None,
                          outputs: Optional[int] = None, table_radius: int = 0, stream: int = 0) -> CellBatch:
         """Batch form of get_cell_at_particle (interface.rs:211-232)."""
