@@ -56,6 +56,23 @@ int main(int argc, char** argv) {
         // a cell around a point that is not a particle (interface.rs:211-232)
         tess::Cell q = diagram.get_cell_at_particle(tess::Vector3{0.31, 0.62, 0.44}, box);
         std::printf("query volume %.17g nfaces %zu\n", q.compute_volume(), q.compute_neighbors().size());
+        // the batch call that streams into host arrays must agree with the per-cell interface
+        {
+            std::vector<double> vol(n), area(64 * n);
+            std::vector<uint64_t> off(n + 1);
+            std::vector<int64_t> nbr(64 * n);
+            std::vector<uint32_t> st(n);
+            auto batch = diagram.compute_all_cells_to_host(vol.data(), off.data(), nbr.data(), area.data(), st.data(), 64 * n, 2);
+            double streamed = 0;
+            for (size_t i = 0; i < n; ++i) streamed += vol[i];
+            tess::Cell c7 = diagram.get_cell_at_index(7, box);
+            c7.compute_voronoi_cell();
+            if (streamed != total || vol[7] != c7.compute_volume() || off[8] - off[7] != c7.compute_neighbors().size()) {
+                std::printf("ERROR: streamed batch differs from the per-cell results\n");
+                return 4;
+            }
+            std::printf("streamed total %.17g\n", streamed);
+        }
         // error behaviour: wrong start polyhedron, add after initialize
         try {
             diagram.get_cell_at_index(0, tess::Polyhedron{0, 0, 0, 2, 2, 2});

@@ -692,7 +692,21 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     const bool streaming = sink && !query && !want_vtx && !d->slab && sink->n_chunks > 1 && n_rows >= (size_t)sink->n_chunks * 1024u;
     const int C = streaming ? sink->n_chunks : 1;
     const uint64_t face_cap = sink ? sink->face_capacity : 0;
-    auto row_begin = [&](int c) { return (size_t)((unsigned long long)n_rows * (unsigned long long)c / (unsigned long long)C); };
+    // Chunk sizes: equal at first, halving towards the end — the copies of the last two chunks are the
+    // only ones that no clip kernel hides, so those chunks are small.
+    std::vector<size_t> chunk_row(C + 1, 0);
+    {
+        std::vector<unsigned long long> w(C);
+        unsigned long long sum = 0;
+        for (int c = 0; c < C; ++c) sum += (w[c] = 1ull << std::min(C - 1 - c, 4));
+        unsigned long long acc = 0;
+        for (int c = 0; c < C; ++c) {
+            acc += w[c];
+            chunk_row[c + 1] = (size_t)((unsigned long long)n_rows * acc / sum);
+        }
+        chunk_row[C] = n_rows;
+    }
+    auto row_begin = [&](int c) { return chunk_row[c]; };
 
     struct Events {
         std::vector<cudaEvent_t> ev;
