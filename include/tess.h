@@ -143,13 +143,15 @@ int tess_compute_all(const tess_diagram* d, const tess_opts* opts, tess_result**
  * groups (0 = default 8); a finished group is packed and copied to the host buffers on a second
  * stream while the next groups are still being computed, so the device->host transfer overlaps the
  * clip kernel (pass page-locked buffers; pageable ones work but do not overlap).
- *   volumes[n], face_offsets[n+1], status[n], neighbors[face_capacity], areas[face_capacity];
- * any pointer may be NULL (areas must be NULL unless TESS_OUT_AREAS is set); more than face_capacity
- * faces -> TESS_ERR_CAPACITY.  The contents equal tess_compute_all + tess_result_download bit for
- * bit; *out holds the same device arrays.  Slab diagrams and tiny inputs are not chunked (one copy at
- * the end); TESS_OUT_VERTICES is not supported here.  On return the host buffers are complete. */
+ *   volumes[cell_capacity], face_offsets[cell_capacity+1], status[cell_capacity],
+ *   neighbors[face_capacity], areas[face_capacity];
+ * any pointer may be NULL (areas must be NULL unless TESS_OUT_AREAS is set); more cells than
+ * cell_capacity or more faces than face_capacity -> TESS_ERR_CAPACITY, nothing is written past them.  The contents equal tess_compute_all + tess_result_download bit for
+ * bit; *out holds the same device arrays (n = the rank's owned cells for slab diagrams).  Tiny inputs
+ * are not chunked (one copy at the end); TESS_OUT_VERTICES is not supported here.  On return the host
+ * buffers are complete. */
 int tess_compute_all_to_host(const tess_diagram* d, const tess_opts* opts, int n_chunks, double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas,
-                             uint32_t* status, uint64_t face_capacity, tess_result** out);
+                             uint32_t* status, uint64_t cell_capacity, uint64_t face_capacity, tess_result** out);
 /* Diagram::get_cell_at_particle (interface.rs:211-232): cells of m arbitrary positions (host,
  * packed f64 triples) that are not particles of the diagram (no self exclusion). */
 int tess_compute_at_points(const tess_diagram* d, const double* xyz, size_t m, const tess_opts* opts, tess_result** out);

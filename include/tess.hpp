@@ -147,14 +147,14 @@ class Diagram {
     /// the same, with the results streamed into caller-owned (ideally page-locked) host arrays while later
     /// cells are still being computed (tess_compute_all_to_host); any pointer may be null
     std::shared_ptr<CellBatch> compute_all_cells_to_host(double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas, uint32_t* status,
-                                                         uint64_t face_capacity, int n_chunks = 0, std::optional<double> search_radius = std::nullopt,
+                                                         uint64_t cell_capacity, uint64_t face_capacity, int n_chunks = 0, std::optional<double> search_radius = std::nullopt,
                                                          std::optional<size_t> target_group = std::nullopt) {
         tess_opts o;
         tess_opts_default(&o);
         if (search_radius) o.search_radius = *search_radius;
         if (target_group) o.target_group = static_cast<int64_t>(*target_group);
         tess_result* r = nullptr;
-        check(tess_compute_all_to_host(d_, &o, n_chunks, volumes, face_offsets, neighbors, (o.outputs & TESS_OUT_AREAS) ? areas : nullptr, status, face_capacity, &r));
+        check(tess_compute_all_to_host(d_, &o, n_chunks, volumes, face_offsets, neighbors, (o.outputs & TESS_OUT_AREAS) ? areas : nullptr, status, cell_capacity, face_capacity, &r));
         return std::make_shared<CellBatch>(r);
     }
     std::shared_ptr<CellBatch> compute_cells_at(const Vector3* pts, size_t m, std::optional<double> search_radius, std::optional<size_t> target_group) {

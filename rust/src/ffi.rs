@@ -38,7 +38,7 @@ extern "C" {
     pub fn tess_diagram_grid_info(d: *const tess_diagram, n_points: *mut u64, cpd: *mut u64, bounds: *mut f64, sizes: *mut f64, inv_sizes: *mut f64) -> c_int;
     pub fn tess_compute_all(d: *const tess_diagram, opts: *const tess_opts, out: *mut *mut tess_result) -> c_int;
     pub fn tess_compute_all_to_host(d: *const tess_diagram, opts: *const tess_opts, n_chunks: c_int, volumes: *mut f64, face_offsets: *mut u64,
-                                    neighbors: *mut i64, areas: *mut f64, status: *mut u32, face_capacity: u64, out: *mut *mut tess_result) -> c_int;
+                                    neighbors: *mut i64, areas: *mut f64, status: *mut u32, cell_capacity: u64, face_capacity: u64, out: *mut *mut tess_result) -> c_int;
     pub fn tess_compute_at_points(d: *const tess_diagram, xyz: *const f64, m: usize, opts: *const tess_opts, out: *mut *mut tess_result) -> c_int;
     pub fn tess_result_free(r: *mut tess_result);
     pub fn tess_result_n_cells(r: *const tess_result, n_cells: *mut u64, n_faces: *mut u64) -> c_int;

@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
             std::vector<uint64_t> off(n + 1);
             std::vector<int64_t> nbr(64 * n);
             std::vector<uint32_t> st(n);
-            auto batch = diagram.compute_all_cells_to_host(vol.data(), off.data(), nbr.data(), area.data(), st.data(), 64 * n, 2);
+            auto batch = diagram.compute_all_cells_to_host(vol.data(), off.data(), nbr.data(), area.data(), st.data(), n, 64 * n, 2);
             double streamed = 0;
             for (size_t i = 0; i < n; ++i) streamed += vol[i];
             tess::Cell c7 = diagram.get_cell_at_index(7, box);

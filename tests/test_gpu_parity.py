@@ -356,6 +356,11 @@ def test_slab_decomposition_is_bit_identical(tess, gen):
             i = ids_out[k]
             assert np.array_equal(sb.cell_neighbors(k), wb.neighbors[wfo[i]:wfo[i + 1]])
             assert np.array_equal(sb.cell_areas(k), wb.areas[wfo[i]:wfo[i + 1]])
+        # the streamed form of the same slab (rows in sorted order: chunks are runs of slots)
+        vol, off, nbr, area, stat = _host_arrays(sb.n_cells, sb.n_faces)
+        d.compute_all_cells_to_host(vol, off, nbr, area, stat, n_chunks=4, outputs=1 | 2 | 4)
+        assert np.array_equal(vol, sb.volumes) and np.array_equal(nbr, sb.neighbors) and np.array_equal(area, sb.areas)
+        assert np.array_equal(off.astype(np.int64), np.asarray(sb.face_offsets).astype(np.int64)) and np.array_equal(stat, sb.status)
         d.close()
     assert seen.all()
     # a halo that is too thin is reported per cell, never silently wrong
@@ -511,6 +516,8 @@ def test_streamed_host_capacity_error_and_optional_arrays(tess, gen):
     vol, off, nbr, area, stat = _host_arrays(ref.n_cells, ref.n_faces // 2)
     with pytest.raises(tess.TessError):
         d.compute_all_cells_to_host(vol, off, nbr, area, stat, n_chunks=4, outputs=ALL_OUT)
+    with pytest.raises(tess.TessError):  # per-cell arrays too short
+        d.compute_all_cells_to_host(vol[:-1], off, nbr, area, stat, n_chunks=4, outputs=ALL_OUT)
     vol, off, nbr, area, stat = _host_arrays(ref.n_cells, ref.n_faces)
     d.compute_all_cells_to_host(vol, None, nbr, None, None, n_chunks=4, outputs=1 | 2)  # volumes + neighbours only
     assert np.array_equal(vol, ref.volumes) and np.array_equal(nbr, ref.neighbors) and np.all(area == -1.0)

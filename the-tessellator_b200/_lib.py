@@ -115,7 +115,7 @@ def lib() -> C.CDLL:
     sig("tess_diagram_copy_grid", ci, vp, vp, vp, vp)
     sig("tess_diagram_copy_search_order", ci, vp, C.c_int32, P(u64), vp, vp, P(ci))
     sig("tess_compute_all", ci, vp, P(Opts), P(vp))
-    sig("tess_compute_all_to_host", ci, vp, P(Opts), ci, vp, vp, vp, vp, vp, C.c_uint64, P(vp))
+    sig("tess_compute_all_to_host", ci, vp, P(Opts), ci, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, P(vp))
     sig("tess_compute_at_points", ci, vp, vp, sz, P(Opts), P(vp))
     sig("tess_result_free", None, vp)
     sig("tess_result_n_cells", ci, vp, P(u64), P(u64))

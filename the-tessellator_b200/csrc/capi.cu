@@ -689,7 +689,8 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     // chunk's rows; and, when streaming, copy them to the host on a second stream.  The clip launch
     // of chunk c+1 is enqueued before chunk c is finished off, so the device never waits for the
     // host, and the copy of chunk c overlaps the clip kernel of chunk c+2.
-    const bool streaming = sink && !query && !want_vtx && !d->slab && sink->n_chunks > 1 && n_rows >= (size_t)sink->n_chunks * 1024u;
+    const bool streaming = sink && !query && !want_vtx && sink->n_chunks > 1 && n_rows >= (size_t)sink->n_chunks * 1024u;
+    const bool listed = streaming && P.row_of_slot != nullptr;  // rows in insertion order: a chunk of rows is a scattered set of slots
     const int C = streaming ? sink->n_chunks : 1;
     const uint64_t face_cap = sink ? sink->face_capacity : 0;
     // Chunk sizes: equal at first, halving towards the end — the copies of the last two chunks are the
@@ -735,9 +736,11 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     uint64_t* pos = nullptr;
     if (streaming) {
         TESS_CUDA_CHECK(cudaStreamCreateWithFlags(&E.copy_stream, cudaStreamNonBlocking));
-        work_list = tmp.get<uint32_t>(n_rows);
-        flags = tmp.get<uint32_t>(n_rows + 1);
-        pos = tmp.get<uint64_t>(n_rows + 1);
+        if (listed) {
+            work_list = tmp.get<uint32_t>(n_rows);
+            flags = tmp.get<uint32_t>(n_rows + 1);
+            pos = tmp.get<uint64_t>(n_rows + 1);
+        }
         r->nbr = dmalloc<int64_t>(face_cap, s);  // the caller's capacity: the total is not known before the last chunk
         if (want_area) r->area = dmalloc<double>(face_cap, s);
     }
@@ -746,12 +749,15 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     auto enqueue_clip = [&](int c) {
         const size_t r0 = row_begin(c), r1 = row_begin(c + 1);
         ClipParams Q = P;
-        if (C > 1) {  // the chunk's cells in ascending slot order
+        if (listed) {  // the chunk's cells in ascending slot order
             launch_chunk_flags(P.row_of_slot, d->own_slot_begin, n_rows, (uint32_t)r0, (uint32_t)r1, flags, s);
             launch_exclusive_scan_u32_to_u64(flags, pos, n_rows + 1, scan_tmp, scan_tmp_bytes(n_rows + 1), s);
             launch_chunk_scatter(flags, pos, d->own_slot_begin, n_rows, work_list + r0, s);
             Q.n_work = (uint32_t)(r1 - r0);
             Q.work_slots = work_list + r0;
+        } else if (C > 1) {  // slab diagrams: rows follow the sorted order, a chunk is a run of slots
+            Q.slot_begin = P.slot_begin + (uint32_t)r0;
+            Q.n_work = (uint32_t)(r1 - r0);
         }
         TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c], s));
         launch_clip(Q, /*large=*/false, s);
@@ -946,7 +952,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         launch_gather_vertices(r->nverts, vbase, r->voffsets, gv_xyz, n_rows, r->vtx, s);
         launch_gather_loops(nloops, lbase, r->offsets, r->fv_offsets, gl_idx, n_rows, r->fv_idx, s);
     }
-    if (sink && !streaming) {  // slab diagrams and small inputs: one copy of the finished arrays
+    if (sink && !streaming) {  // small inputs: one copy of the finished arrays
         const int rc = tess_result_download(r.get(), sink->volumes, sink->face_offsets, sink->neighbors, want_area ? sink->areas : nullptr, sink->status, s);
         if (rc != TESS_OK) return rc;
     }
@@ -980,12 +986,14 @@ int tess_compute_all(const tess_diagram* d, const tess_opts* opts, tess_result**
 }
 
 int tess_compute_all_to_host(const tess_diagram* d, const tess_opts* opts, int n_chunks, double* volumes, uint64_t* face_offsets, int64_t* neighbors, double* areas,
-                             uint32_t* status, uint64_t face_capacity, tess_result** out) {
+                             uint32_t* status, uint64_t cell_capacity, uint64_t face_capacity, tess_result** out) {
     if (!d || !out) return fail(TESS_ERR_INVALID, "NULL argument");
     *out = nullptr;
     if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
     if (opts && (opts->outputs & TESS_OUT_VERTICES)) return fail(TESS_ERR_INVALID, "tess_compute_all_to_host does not stream vertex geometry; use tess_compute_all");
     if (n_chunks < 0 || n_chunks > 256) return fail(TESS_ERR_INVALID, "n_chunks must be in [0, 256]");
+    if (static_cast<uint64_t>(d->own_slot_end - d->own_slot_begin) > cell_capacity)
+        return fail(TESS_ERR_CAPACITY, "tess_compute_all_to_host: the diagram has more cells than cell_capacity");
     TESS_TRY
     HostSink sink{volumes, face_offsets, neighbors, areas, status, face_capacity, n_chunks == 0 ? 8 : n_chunks};
     return compute_impl(d, opts, nullptr, 0, out, &sink);

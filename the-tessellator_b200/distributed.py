@@ -156,7 +156,12 @@ class CudaSlabBackend(SlabBackend):
         s = self._stream()
         d.add_particles_device(xyz.data_ptr(), xyz.shape[0], ids_ptr=ids.data_ptr(), stream=s)
         d.initialize_slab(Polyhedron(*box), bounds6, n_global, own, local, stream=s)
-        batch = d.compute_all_cells(stream=s, **opts)
+        opts = dict(opts)
+        sink = opts.pop("host_sink", None)
+        if sink is None:
+            batch = d.compute_all_cells(stream=s, **opts)
+        else:  # (volumes, face_offsets, neighbors, areas, status[, n_chunks]): results stream to the rank's host arrays
+            batch = d.compute_all_cells_to_host(*sink[:5], n_chunks=(sink[5] if len(sink) > 5 else 0), stream=s, **opts)
         flagged = False
         if batch.n_cells:
             # status words stay on the device: one tiny reduction tells whether any halo was too thin

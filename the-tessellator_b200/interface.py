@@ -320,7 +320,7 @@ class Diagram:
         still being computed (tess_compute_all_to_host).  Each argument is a C-contiguous host array of the
         right dtype — numpy, or anything with `data_ptr()` / `numel()` such as a pinned torch tensor — or None:
         volumes f64[n], face_offsets u64/i64[n+1], neighbors i64[cap], areas f64[cap], status u32/i32[n]; the
-        capacity in faces is the smaller of len(neighbors) and len(areas).  Page-locked arrays overlap the copy
+        capacities in cells and faces are taken from the array lengths (too short -> TessError, nothing overrun).  Page-locked arrays overlap the copy
         with the compute.  Returns the device-side batch; the host arrays are complete on return."""
         def ptr_len(a, itemsize):
             if a is None:
@@ -335,15 +335,13 @@ class Diagram:
         pn, nn = ptr_len(neighbors, 8)
         pa, na = ptr_len(areas, 8)
         ps, ns = ptr_len(status, 4)
-        n = self._n
-        if (nv is not None and nv < n) or (no is not None and no < n + 1) or (ns is not None and ns < n):
-            raise ValueError("compute_all_cells_to_host: per-cell arrays are too short")
+        cell_caps = [c for c in (nv, None if no is None else no - 1, ns) if c is not None]
         caps = [c for c in (nn, na) if c is not None]
         o = self._opts(search_radius, target_group, outputs, table_radius, stream)
         if pa is not None and not (o.outputs & _lib.OUT_AREAS):
             pa = None
         h = C.c_void_p(0)
-        check(_lib.lib().tess_compute_all_to_host(self._h, C.byref(o), int(n_chunks), pv, po, pn, pa, ps, min(caps) if caps else 0, C.byref(h)))
+        check(_lib.lib().tess_compute_all_to_host(self._h, C.byref(o), int(n_chunks), pv, po, pn, pa, ps, min(cell_caps) if cell_caps else 2**62, min(caps) if caps else 0, C.byref(h)))
         return CellBatch(h.value, self.device)
 
     def compute_cells_at(self, points: np.ndarray, search_radius: Optional[float] = None, target_group: Optional[int] = None,
