@@ -1,0 +1,121 @@
+"""The clip kernel SOURCE (the-tessellator_b200/csrc/clip.cu, unchanged) run lane by lane on the CPU warp emulator
+(tests/emu/) against the oracle.  This is test infrastructure: it lets the CPU-only suite exercise every path of
+the kernel — lane-parallel cut through the adjacency lists, table-sweep variant, serial walk, large-cell
+configuration, radius and group modes — bit for bit, and it checks two things a GPU run cannot show:
+every warp collective is reached by all 32 lanes from the same source line, and results do not depend on the
+order in which the lanes run between two collectives (forward 0..31 and reverse 31..0 schedules)."""
+import numpy as np
+import pytest
+
+import helpers
+
+BOX = (0, 0, 0, 1, 1, 1)
+BAD = 0x2 | 0x4 | 0x10  # TABLE_EXHAUSTED | CAPACITY_OVERFLOW | INCONSISTENT: cells the product re-runs
+
+
+@pytest.fixture(scope="module")
+def eb():
+    import emu_binding
+
+    emu_binding.lib()
+    return emu_binding
+
+
+class _Rows:
+    def __init__(self, r, mask):
+        fo = np.asarray(r.face_offsets, np.int64)
+        cnt = np.diff(fo)[mask]
+        self.volumes = np.asarray(r.volumes)[mask]
+        self.face_offsets = np.concatenate([[0], np.cumsum(cnt)])
+        sel = np.repeat(mask, np.diff(fo))
+        self.neighbors = np.asarray(r.neighbors)[sel]
+        self.areas = np.asarray(r.areas)[sel]
+
+
+def _check(e, r, what, expect_all=True):
+    ok = (e.status & BAD) == 0
+    if expect_all:
+        assert ok.all(), f"{what}: {int((~ok).sum())} cells not finished"
+    helpers.assert_cells_identical(_Rows(e, ok), _Rows(r, ok), what=what)
+    assert np.array_equal(e.status[ok], r.status[ok]), what
+    return ok
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "bcc", "tiny", "on_walls", "duplicates"])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_small_configuration_matches_oracle(eb, gen, case, reverse):
+    base = gen.uniform(1500, 81)
+    pts = {
+        "uniform": lambda: gen.uniform(3000, 51),
+        "clustered": lambda: gen.clustered(3000, 4, k=4),
+        "bcc": lambda: gen.bcc(10, 5),
+        "tiny": lambda: gen.uniform(5, 52),
+        "on_walls": lambda: np.concatenate([base, np.round(gen.uniform(200, 82), 0) * np.array([1, 1, 0]) + gen.uniform(200, 83) * np.array([0, 0, 1])]),
+        "duplicates": lambda: np.concatenate([base, base[:100], base[:20]]),
+    }[case]()
+    g = eb.EmuGrid(pts, BOX, table_radius=-1 if case in ("tiny", "clustered") else 8)
+    e = g.clip(reverse=reverse)
+    r = g.oracle_cells()
+    ok = _check(e, r, case, expect_all=case != "clustered")
+    assert ok.mean() > 0.95
+    if ok.all():
+        for k in ("visited", "tested", "vertex_classifications", "cuts", "new_vertices", "table_entries", "degenerate_skips", "faces"):
+            assert e.counters[k] == r.counters[k], k
+    assert np.array_equal(e.cell_id, g.sorted_indices)
+
+
+@pytest.mark.parametrize("flags", [1, 2])
+def test_cut_variants_are_identical(eb, gen, flags):
+    """flags bit 0: serial walk only (TESS_FORCE_SERIAL), bit 1: table sweep instead of adjacency lists."""
+    pts = np.concatenate([gen.uniform(1500, 5), gen.bcc(6, 5)])
+    g = eb.EmuGrid(pts, BOX)
+    r = g.oracle_cells()
+    _check(g.clip(flags=flags), r, f"flags {flags}")
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_exact_ties_take_the_serial_walk(eb, gen, reverse):
+    """Un-jittered lattices: bisectors through vertices and edges (Incident vertices, valence > 3, SURVEY D17 skips)."""
+    for pts in (gen.simple_cubic(6), gen.bcc(5, 5, jitter=0.0)):
+        g = eb.EmuGrid(pts, BOX, table_radius=-1)
+        e = g.clip(reverse=reverse)
+        r = g.oracle_cells()
+        _check(e, r, "lattice")
+        assert e.counters["degenerate_skips"] == r.counters["degenerate_skips"]
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_large_configuration(eb, gen, reverse):
+    """A particle inside a dense shell (hundreds of faces) overflows the small tables and is redone by LargeCfg."""
+    u = gen.uniform(150, 54)
+    th, ph = np.arccos(2 * u[:, 0] - 1), 2 * np.pi * u[:, 1]
+    shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
+    bg = gen.uniform(600, 55)
+    pts = np.concatenate([[[0.5, 0.5, 0.5]], shell, bg[np.linalg.norm(bg - 0.5, axis=1) > 0.35]])
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    e = g.clip(reverse=reverse)
+    assert e.n_failed >= 1 and (e.status & 0x4).any()  # the centre cell does not fit the small tables
+    r = g.oracle_cells()
+    _check(e, r, "small pass", expect_all=False)
+    slots = np.sort(e.failed_slots)
+    el = g.clip(work_slots=slots, large=True, reverse=reverse)
+    rl = g.oracle_cells(slots=slots)
+    assert max(np.diff(rl.face_offsets)) > 64
+    _check(el, rl, "large pass")
+    # and the large configuration on ordinary cells
+    some = np.arange(0, g.n, 7, dtype=np.uint32)
+    _check(g.clip(work_slots=some, large=True, reverse=reverse), g.oracle_cells(slots=some), "large on ordinary cells")
+
+
+def test_reference_radius_and_group_modes(eb, gen, ob):
+    pts = gen.uniform(2000, 57)
+    groups = (np.arange(len(pts)) % 3).astype(np.uint64)
+    g = eb.EmuGrid(pts, BOX, groups=groups, table_radius=-1)
+    sx = g.cell_info[0]
+    for radius in (0.0, (1.5 * sx) ** 2):
+        e = g.clip(search_radius=radius)
+        r = g.oracle_cells(mode=ob.MODE_REFERENCE_RADIUS, search_radius=radius)
+        _check(e, r, f"radius {radius}")
+        assert e.counters["tested"] == r.counters["tested"]
+    for tg in (0, 2):
+        _check(g.clip(target_group=tg), g.oracle_cells(target_group=tg), f"group {tg}")

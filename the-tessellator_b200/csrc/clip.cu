@@ -37,6 +37,15 @@ namespace {
 
 constexpr uint32_t FULL = 0xffffffffu;
 
+// A warp-uniform region: code that all 32 lanes of the (converged) warp execute redundantly on the same
+// shared-memory state — every lane reads the same words and writes the same values.  The markers compile
+// to nothing here; the CPU warp emulator of the test suite (tests/emu) uses them to give each lane the
+// state the first lane found and to check that all lanes leave the region with identical state.
+#ifndef TESS_UNIFORM_BEGIN
+#define TESS_UNIFORM_BEGIN(ptr, bytes) ((void)0)
+#define TESS_UNIFORM_END() ((void)0)
+#endif
+
 // Start cube: {flip, target, next} of the 24 half-edges (ids of polyhedron.rs:97-199)
 __constant__ uint32_t kCubeEdges[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x050200u, 0x110205u, 0x030106u, 0x170507u, 0x090604u,
                                         0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
@@ -762,9 +771,13 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 
     // ---- the walk (polyhedron.rs:475-623), warp-uniform ---------------------------------------
     M.simple = false;  // vertices created here are not entered into vout[] (and may have valence > 3)
+    TESS_UNIFORM_BEGIN(sm, sizeof(*sm));
     const int cap_first = M.alloc_edge();
     const int cap_face = M.alloc_face();
-    if (cap_first < 0 || cap_face < 0) return -1;
+    if (cap_first < 0 || cap_face < 0) {
+        TESS_UNIFORM_END();
+        return -1;
+    }
     sm->fnbr[cap_face] = neighbor_id;  // Face.point_index (polyhedron.rs:479-482)
     sm->fstart[cap_face] = (typename Cfg::Idx)cap_first;
     sm->edge[cap_first] = MeshT::pack(Cfg::NONE, Cfg::NONE, Cfg::NONE, (uint32_t)cap_face);
@@ -780,6 +793,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     // (Plane::intersection, or the copy of an Incident vertex) is computed afterwards, one lane per
     // crossing: coordinates of NEW vertices are never read while walking.
     auto emit_vertices = [&](uint32_t count) {
+        TESS_UNIFORM_END();
         __syncwarp();
         if ((uint32_t)lane < count) {
             const EW rec = sm->xlist[lane];
@@ -795,6 +809,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             sm->vz[nv] = x.z;
         }
         __syncwarp();
+        TESS_UNIFORM_BEGIN(sm, sizeof(*sm));
     };
 
     do {
@@ -814,13 +829,17 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             cv = MeshT::e_tgt(w_cur);
             if (--budget < 0) {
                 status |= ST_INCONSISTENT;
+                TESS_UNIFORM_END();
                 return -2;
             }
         }
         if (need) {  // :552-601
             const int nv = M.vlive.alloc(Cfg::VMAX);
             const int br = M.alloc_edge();
-            if (nv < 0 || br < 0) return -1;
+            if (nv < 0 || br < 0) {
+                TESS_UNIFORM_END();
+                return -1;
+            }
             M.note_vertex(nv);
             sm->xlist[nbridge & 31u] = MeshT::pack(pv, cv, (uint32_t)nv, M.outside.test(pv) ? 0u : 1u);
             const uint32_t f = MeshT::e_face(w_out);
@@ -831,7 +850,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
             M.set_field(cap_cur, 1, (uint32_t)br);
             sm->edge[out_e] = MeshT::pack((uint32_t)br, MeshT::e_flip(w_out), prev_int, f);  // :550 + :590
             const int nc = M.alloc_edge();
-            if (nc < 0) return -1;
+            if (nc < 0) {
+                TESS_UNIFORM_END();
+                return -1;
+            }
             sm->edge[nc] = MeshT::pack(cap_cur, Cfg::NONE, (uint32_t)nv, (uint32_t)cap_face);
             cap_cur = (uint32_t)nc;
             prev_int = (uint32_t)nv;
@@ -843,6 +865,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         out_e = MeshT::e_flip(w_cur);  // :603-607
         if (--budget < 0) {
             status |= ST_INCONSISTENT;
+            TESS_UNIFORM_END();
             return -2;
         }
     } while (out_e != (uint32_t)first);  // :620-622
@@ -861,6 +884,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
         sm->estack[M.e_top] = (typename Cfg::Idx)redundant;
         M.e_top += 1;
     }
+    TESS_UNIFORM_END();
     __syncwarp();
 
     // ---- retire what was cut off (clean_up_vertices / clean_up_edges / mark_sweep,
@@ -890,6 +914,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
                     }
                 }
                 uint32_t am = __ballot_sync(FULL, add_v != Cfg::NONE);
+                TESS_UNIFORM_BEGIN(sm, sizeof(*sm));
                 while (am) {  // rare: serialise
                     const int l = __ffs(am) - 1;
                     am &= am - 1;
@@ -899,6 +924,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
                         changed = true;
                     }
                 }
+                TESS_UNIFORM_END();
             }
         }
     }
@@ -967,7 +993,11 @@ template <class Cfg, bool COUNT>
 __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const ClipParams P) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
+#ifdef TESS_WARP_EMU  // tests/emu: this source run lane by lane on the CPU (test infrastructure only)
+    unsigned char* smem_raw = emu::dynamic_smem();
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     WarpSmem<Cfg>* sm = reinterpret_cast<WarpSmem<Cfg>*>(smem_raw) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     MeshT M;
@@ -1337,6 +1367,10 @@ template <class Cfg, bool COUNT>
 void launch_cfg(const ClipParams& p, cudaStream_t s) {
     if (!p.n_work) return;
     const size_t smem = sizeof(WarpSmem<Cfg>) * Cfg::WARPS;
+#ifdef TESS_WARP_EMU
+    *p.work_counter = 0u;
+    emu_launch_kernel([](const void* a) { clip_kernel<Cfg, COUNT>(*static_cast<const ClipParams*>(a)); }, &p, Cfg::WARPS * 32, smem);
+#else
     static bool configured = false;
     static int per_sm_cached = 0, sms_cached = 0;
     if (!configured) {
@@ -1356,6 +1390,7 @@ void launch_cfg(const ClipParams& p, cudaStream_t s) {
     clip_kernel<Cfg, COUNT><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
+#endif
 }
 
 }  // namespace
