@@ -126,6 +126,14 @@ int emu_clip_run(emu_clip_args* a) {
     return 0;
 }
 
+// profile of the last launches: how often each warp collective (by clip.cu source line) was executed
+static unsigned long long g_hist[65536];
+void emu_line_hist_enable(int on) {
+    memset(g_hist, 0, sizeof(g_hist));
+    emu::g_line_hist = on ? g_hist : nullptr;
+}
+const unsigned long long* emu_line_hist() { return g_hist; }
+
 uint32_t emu_small_fmax() { return tess::clip_small_fmax(); }
 uint32_t emu_large_fmax() { return tess::clip_large_fmax(); }
 }

@@ -35,6 +35,7 @@ emu_switch:
 namespace emu {
 
 thread_local Block* tl_block = nullptr;
+unsigned long long* g_line_hist = nullptr;
 
 void fiber_trampoline() {
     Block* b = tl_block;
@@ -120,6 +121,7 @@ LaunchStats launch(void (*entry)(const void*), const void* arg, unsigned nblocks
         b.arg = arg;
         b.nblocks = nblocks;
         b.nthreads = nthreads;
+        b.line_hist = os_threads == 1 ? g_line_hist : nullptr;
         for (;;) {
             const unsigned id = next.fetch_add(1);
             if (id >= nblocks) break;

@@ -54,6 +54,7 @@ struct Block {
     const void* arg = nullptr;
     unsigned bid = 0, nblocks = 0, nthreads = 0;
     unsigned long long collectives = 0;
+    unsigned long long* line_hist = nullptr;  // optional: executions of each collective by source line (65536 entries)
 };
 extern thread_local Block* tl_block;
 
@@ -130,7 +131,10 @@ inline const uint64_t* rendezvous(uint64_t v, uint32_t tag) {
     const unsigned nb = (f->lane + 1u) & 31u;
     if (w->seq[k][nb] != my_seq) die("lanes disagree on the number of collectives executed", (int)(tag & 0xFFFFFu), (int)(w->tag[k][nb] & 0xFFFFFu));
     if (w->tag[k][nb] != tag) die("lanes meet in different collectives (divergent call sites)", (int)(tag & 0xFFFFFu), (int)(w->tag[k][nb] & 0xFFFFFu));
-    if (f->lane == 0) b->collectives++;
+    if (f->lane == 0) {
+        b->collectives++;
+        if (b->line_hist) b->line_hist[tag & 0xFFFFu]++;
+    }
     return w->buf[k];
 }
 
@@ -248,6 +252,8 @@ void fiber_trampoline();
 struct LaunchStats {
     unsigned long long collectives = 0;
 };
+// when set (single host thread only), every launch adds its per-source-line collective counts here
+extern unsigned long long* g_line_hist;
 
 // Runs `entry(arg)` as a grid of `nblocks` CTAs of `nthreads` threads; CTAs are spread over
 // `os_threads` host threads.  `reverse`: lanes of a warp are resumed 31..0 instead of 0..31.
