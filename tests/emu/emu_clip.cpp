@@ -57,6 +57,16 @@ struct emu_clip_args {
     uint64_t* counters;     // 8, nullable
     uint32_t* failed_slots; // n_work, nullable
     uint32_t* n_failed;     // 8
+    // optional geometry outputs (TESS_OUT_VERTICES): pools + per-row records, all nullable together
+    double* gv_xyz;
+    uint32_t* gl_idx;
+    uint64_t gv_cap, gl_cap;
+    uint64_t* g_cursor;     // 2
+    uint32_t* nverts;
+    uint32_t* nloops;
+    uint64_t* vbase;
+    uint64_t* lbase;
+    uint16_t* st_flen;
     // emulator
     uint32_t os_threads, blocks, reverse;
     uint64_t collectives;   // out
@@ -115,6 +125,11 @@ int emu_clip_run(emu_clip_args* a) {
     P.n_failed = a->n_failed;
     P.failed_cap = a->n_work;
     P.flags = a->flags;
+    P.gv_xyz = a->gv_xyz; P.gl_idx = a->gl_idx; P.gv_cap = a->gv_cap; P.gl_cap = a->gl_cap;
+    P.g_cursor = reinterpret_cast<unsigned long long*>(a->g_cursor);
+    P.nverts = a->nverts; P.nloops = a->nloops;
+    P.vbase = reinterpret_cast<unsigned long long*>(a->vbase); P.lbase = reinterpret_cast<unsigned long long*>(a->lbase);
+    P.st_flen = a->st_flen;
     g_os_threads = a->os_threads ? a->os_threads : 1;
     g_blocks = a->blocks ? a->blocks : g_os_threads;
     g_reverse = a->reverse != 0;

@@ -23,8 +23,10 @@ class Args(C.Structure):
         ("box", C.c_double * 6), ("groups_sorted", C.c_void_p), ("work_slots", C.c_void_p), ("n_work", C.c_uint32), ("query_xyz", C.c_void_p),
         ("target_group", C.c_int64), ("search_radius", C.c_double), ("flags", C.c_uint32), ("large", C.c_int32), ("fstride", C.c_uint32),
         ("vol", C.c_void_p), ("nfaces", C.c_void_p), ("status", C.c_void_p), ("cell_id", C.c_void_p), ("st_nbr", C.c_void_p), ("st_area", C.c_void_p),
-        ("counters", C.c_void_p), ("failed_slots", C.c_void_p), ("n_failed", C.c_void_p), ("os_threads", C.c_uint32), ("blocks", C.c_uint32),
-        ("reverse", C.c_uint32), ("collectives", C.c_uint64),
+        ("counters", C.c_void_p), ("failed_slots", C.c_void_p), ("n_failed", C.c_void_p),
+        ("gv_xyz", C.c_void_p), ("gl_idx", C.c_void_p), ("gv_cap", C.c_uint64), ("gl_cap", C.c_uint64), ("g_cursor", C.c_void_p),
+        ("nverts", C.c_void_p), ("nloops", C.c_void_p), ("vbase", C.c_void_p), ("lbase", C.c_void_p), ("st_flen", C.c_void_p),
+        ("os_threads", C.c_uint32), ("blocks", C.c_uint32), ("reverse", C.c_uint32), ("collectives", C.c_uint64),
     ]
 
 
@@ -54,6 +56,18 @@ class EmuCells:
         self.failed_slots = failed_slots[: self.n_failed].copy()
         self.collectives = int(collectives)
 
+    def cell_vertices(self, c):
+        """Cell::compute_vertices of row c (cell-local coordinates, ascending vertex-slot order)."""
+        g = self.geo
+        return g["gv"][int(g["vb"][c]): int(g["vb"][c]) + int(g["nv"][c])]
+
+    def face_loop(self, c, j):
+        """VoronoiFace::compute_vertices of the j-th face (face-slot order) of row c."""
+        g = self.geo
+        lens = g["fl"].reshape(-1, self.fstride)[c, : int(self.nfaces[c])].astype(np.int64)
+        off = int(g["lb"][c]) + int(lens[:j].sum())
+        return self.cell_vertices(c)[g["gl"][off: off + int(lens[j])]]
+
 
 class EmuGrid:
     """The grid arrays the clip kernel reads, taken from the oracle (tests elsewhere pin the CUDA binning
@@ -78,12 +92,17 @@ class EmuGrid:
         self.groups_sorted = None if groups is None else np.ascontiguousarray(np.asarray(groups, np.uint64)[self.sorted_indices])
         assert self.delim.size == self.cpd ** 3 + 1
 
-    def clip(self, work_slots=None, large=False, flags=0, search_radius=float("nan"), target_group=-1, os_threads=8, reverse=False, fstride=None):
+    def clip(self, work_slots=None, large=False, flags=0, search_radius=float("nan"), target_group=-1, os_threads=8, reverse=False, fstride=None,
+             query_xyz=None, want_vertices=False):
         L = lib()
         if fstride is None:
             fstride = int(L.emu_large_fmax()) if large else 40
         ws = None if work_slots is None else np.ascontiguousarray(work_slots, np.uint32)
         m = self.n if ws is None else ws.size
+        q = None
+        if query_xyz is not None:  # get_cell_at_particle: one cell per query position, no self exclusion
+            q = np.ascontiguousarray(query_xyz, np.float64).reshape(-1, 3)
+            m = q.shape[0]
         vol, nfaces, status, cell_id = np.zeros(m), np.zeros(m, np.uint32), np.zeros(m, np.uint32), np.zeros(m, np.int64)
         st_nbr, st_area = np.zeros(m * fstride, np.int64), np.zeros(m * fstride)
         counters, failed, n_failed = np.zeros(8, np.uint64), np.zeros(max(m, 1), np.uint32), np.zeros(8, np.uint32)
@@ -93,7 +112,15 @@ class EmuGrid:
         a.bounds, a.cell_info, a.cpd = (C.c_double * 6)(*self.bounds), (C.c_double * 6)(*self.cell_info), self.cpd
         a.box = (C.c_double * 6)(*self.box)
         a.groups_sorted = None if self.groups_sorted is None else self.groups_sorted.ctypes.data
-        a.work_slots, a.n_work, a.query_xyz = (None if ws is None else ws.ctypes.data), m, None
+        a.work_slots, a.n_work, a.query_xyz = (None if ws is None else ws.ctypes.data), m, (None if q is None else q.ctypes.data)
+        geo = None
+        if want_vertices:
+            vmax = 1024 if large else 64
+            geo = dict(gv=np.zeros((m * vmax, 3)), gl=np.zeros(m * 3 * vmax, np.uint32), cur=np.zeros(2, np.uint64), nv=np.zeros(m, np.uint32),
+                       nl=np.zeros(m, np.uint32), vb=np.zeros(m, np.uint64), lb=np.zeros(m, np.uint64), fl=np.zeros(m * fstride, np.uint16))
+            a.gv_xyz, a.gl_idx, a.gv_cap, a.gl_cap = geo["gv"].ctypes.data, geo["gl"].ctypes.data, m * vmax, m * 3 * vmax
+            a.g_cursor, a.nverts, a.nloops = geo["cur"].ctypes.data, geo["nv"].ctypes.data, geo["nl"].ctypes.data
+            a.vbase, a.lbase, a.st_flen = geo["vb"].ctypes.data, geo["lb"].ctypes.data, geo["fl"].ctypes.data
         a.target_group, a.search_radius, a.flags, a.large, a.fstride = target_group, search_radius, flags, int(large), fstride
         a.vol, a.nfaces, a.status, a.cell_id = vol.ctypes.data, nfaces.ctypes.data, status.ctypes.data, cell_id.ctypes.data
         a.st_nbr, a.st_area, a.counters = st_nbr.ctypes.data, st_area.ctypes.data, counters.ctypes.data
@@ -101,7 +128,11 @@ class EmuGrid:
         a.os_threads, a.blocks, a.reverse = os_threads, os_threads, int(reverse)
         rc = L.emu_clip_run(C.byref(a))
         assert rc == 0
-        return EmuCells(vol, nfaces, status, cell_id, st_nbr, st_area, fstride, counters, n_failed, failed, a.collectives)
+        e = EmuCells(vol, nfaces, status, cell_id, st_nbr, st_area, fstride, counters, n_failed, failed, a.collectives)
+        if geo is not None:
+            e.geo = geo
+            e.fstride = fstride
+        return e
 
     def oracle_cells(self, slots=None, **kw):
         """The oracle's cells in the kernel's row order (grid order, or the given sorted slots)."""

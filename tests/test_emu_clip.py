@@ -119,3 +119,34 @@ def test_reference_radius_and_group_modes(eb, gen, ob):
         assert e.counters["tested"] == r.counters["tested"]
     for tg in (0, 2):
         _check(g.clip(target_group=tg), g.oracle_cells(target_group=tg), f"group {tg}")
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_vertex_lists_and_face_loops(eb, gen, large):
+    """TESS_OUT_VERTICES: per-face ordered vertex loops bit-identical to
+    Polyhedron::compute_face_vertices; the cell's vertex list is the same set of points."""
+    pts = gen.uniform(1200, 64)
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    slots = np.arange(0, g.n, 3 if large else 1, dtype=np.uint32)
+    e = g.clip(work_slots=slots, large=large, want_vertices=True)
+    r = g.oracle_cells(slots=slots, want_vertices=True)
+    _check(e, r, "geometry")
+    assert np.array_equal(e.geo["nv"], np.diff(r.vertex_offsets))
+    fo = r.face_offsets
+    for c in range(0, len(slots), 7):
+        assert {tuple(v) for v in e.cell_vertices(c)} == {tuple(v) for v in r.cell_vertices(c)}
+        for j in range(int(fo[c + 1] - fo[c])):
+            assert np.array_equal(e.face_loop(c, j), r.face_loop(int(fo[c]) + j)), (c, j)
+
+
+def test_cells_at_query_points(eb, gen):
+    """get_cell_at_particle (interface.rs:211-232): a cell around an arbitrary position, no self exclusion."""
+    pts = gen.uniform(2000, 59)
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    q = gen.uniform(48, 60)
+    e = g.clip(query_xyz=q)
+    for i in range(len(q)):
+        r = g.oracle.compute_cell_at_point(*q[i])
+        nf = int(e.nfaces[i])
+        assert e.neighbors[e.face_offsets[i]: e.face_offsets[i] + nf].tolist() == r.neighbors.tolist()
+        assert e.volumes[i] == r.volumes[0] and np.array_equal(e.areas[e.face_offsets[i]: e.face_offsets[i] + nf], r.areas)

@@ -137,6 +137,11 @@ struct SmemMask {
 #ifndef TESS_CLIP_MINBLOCKS
 #define TESS_CLIP_MINBLOCKS 5  // resident CTAs per SM the small kernel is compiled for (register cap)
 #endif
+// A staged tile with at least this many candidates waiting is screened candidate-parallel before the planes
+// are offered one by one (0 disables the screen); see the comment at its use.
+#ifndef TESS_PREFILTER_MIN
+#define TESS_PREFILTER_MIN 8
+#endif
 struct SmallCfg {
     static constexpr int MINB = TESS_CLIP_MINBLOCKS;
     static constexpr int VMAX = 64, EMAX = 256, FMAX = 64;
@@ -1119,11 +1124,49 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 }
                 __syncwarp();
                 uint32_t pending = __ballot_sync(FULL, cand && !(src_key > stop_thr));
+                // Screen (not in the reference, results unchanged): with many candidates waiting, every lane
+                // first tests ITS plane against all live vertices.  A plane that keeps every vertex of the
+                // current polytope inside by a margin far above any rounding error (1e-9 of the cell's radius;
+                // later vertices are convex combinations of these, each off by a few ulp) can never have a
+                // vertex Outside: find_outgoing_edge (polyhedron.rs:399-410) would return None for it whenever
+                // it is offered, so the one-plane-at-a-time classification is skipped for it (it still counts
+                // as tested).  Dense tiles of clustered inputs lose most of their non-cutting planes here.
+                uint32_t nocut = 0;
+                if (TESS_PREFILTER_MIN > 0 && !radius_mode && __popc(pending) >= TESS_PREFILTER_MIN) {
+                    const double mar = mul(1e-9, __dsqrt_rn(stop_thr));
+                    bool clear_of_all = false;
+                    if (((pending >> lane) & 1u) && !src_marker) {
+                        clear_of_all = true;
+                        const double4 q = sm->cand_plane[lane];
+                        const double thr = subd(q.w, mar);
+#pragma unroll
+                        for (int p = 0; p < MeshT::NWV; ++p) {
+                            if (p >= M.nwv()) break;
+                            for (uint32_t m = M.vlive.word(p); m; m &= m - 1u) {
+                                const int v = 32 * p + __ffs(m) - 1;
+                                const double d = __fma_rn(q.x, sm->vx[v], __fma_rn(q.y, sm->vy[v], mul(q.z, sm->vz[v])));
+                                clear_of_all = clear_of_all && (d < thr);  // false for NaN planes too: those take the normal path
+                            }
+                        }
+                    }
+                    nocut = __ballot_sync(FULL, clear_of_all);
+                }
                 while (pending) {
                     const int l = __ffs(pending) - 1;
                     pending &= pending - 1;
                     if (__shfl_sync(FULL, (int)src_marker, l)) {
                         status |= ST_HALO_INSUFFICIENT;
+                        continue;
+                    }
+                    if ((nocut >> l) & 1u) {  // screened out above: tested, every vertex classified Inside, no cut
+                        if (COUNT) {
+                            c_test += 1;
+#pragma unroll
+                            for (int p = 0; p < MeshT::NWV; ++p) {
+                                if (p >= M.nwv()) break;
+                                c_vc += __popc(M.vlive.word(p));
+                            }
+                        }
                         continue;
                     }
                     const double4 pq = sm->cand_plane[l];  // broadcast read
