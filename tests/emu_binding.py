@@ -93,7 +93,8 @@ class EmuGrid:
         assert self.delim.size == self.cpd ** 3 + 1
 
     def clip(self, work_slots=None, large=False, flags=0, search_radius=float("nan"), target_group=-1, os_threads=8, reverse=False, fstride=None,
-             query_xyz=None, want_vertices=False):
+             query_xyz=None, want_vertices=False, count=True):
+        """count=False runs the instantiation without work counters (the one the product times)."""
         L = lib()
         if fstride is None:
             fstride = int(L.emu_large_fmax()) if large else 40
@@ -123,7 +124,7 @@ class EmuGrid:
             a.vbase, a.lbase, a.st_flen = geo["vb"].ctypes.data, geo["lb"].ctypes.data, geo["fl"].ctypes.data
         a.target_group, a.search_radius, a.flags, a.large, a.fstride = target_group, search_radius, flags, int(large), fstride
         a.vol, a.nfaces, a.status, a.cell_id = vol.ctypes.data, nfaces.ctypes.data, status.ctypes.data, cell_id.ctypes.data
-        a.st_nbr, a.st_area, a.counters = st_nbr.ctypes.data, st_area.ctypes.data, counters.ctypes.data
+        a.st_nbr, a.st_area, a.counters = st_nbr.ctypes.data, st_area.ctypes.data, (counters.ctypes.data if count else None)
         a.failed_slots, a.n_failed = failed.ctypes.data, n_failed.ctypes.data
         a.os_threads, a.blocks, a.reverse = os_threads, os_threads, int(reverse)
         rc = L.emu_clip_run(C.byref(a))

@@ -64,6 +64,17 @@ def test_small_configuration_matches_oracle(eb, gen, case, reverse):
     assert np.array_equal(e.cell_id, g.sorted_indices)
 
 
+@pytest.mark.parametrize("case", ["uniform", "clustered", "bcc"])
+def test_kernel_without_counters(eb, gen, case):
+    """The instantiation the product times (COUNT=false): screened-out planes leave the candidate queue at once."""
+    pts = {"uniform": lambda: gen.uniform(3000, 61), "clustered": lambda: gen.clustered(4000, 4, k=4), "bcc": lambda: gen.bcc(9, 5)}[case]()
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    e = g.clip(count=False)
+    ok = _check(e, g.oracle_cells(), case, expect_all=False)
+    assert ok.mean() > 0.95
+    assert all(v == 0 for v in e.counters.values())
+
+
 @pytest.mark.parametrize("flags", [1, 2])
 def test_cut_variants_are_identical(eb, gen, flags):
     """flags bit 0: serial walk only (TESS_FORCE_SERIAL), bit 1: table sweep instead of adjacency lists."""

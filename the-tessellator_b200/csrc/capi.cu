@@ -169,7 +169,7 @@ struct tess_diagram {
     GridSpec grid{};
     double box[6] = {0, 0, 0, 0, 0, 0};
     size_t n_cells_local = 0;
-    DevBuf counts, delim, cell_of, rank_in_cell, tmp_idx, sorted, sorted_idx, slot_of, groups_sorted, scan_tmp, small;
+    DevBuf counts, delim, cell_of, rank_in_cell, tmp_idx, arrived, sorted, sorted_idx, groups_sorted, scan_tmp, small;
     uint32_t own_slot_begin = 0, own_slot_end = 0;
     cudaEvent_t ev_bin0 = nullptr, ev_bin1 = nullptr;  // around K2-K4 of the last initialize
     mutable std::mutex mu;
@@ -300,7 +300,7 @@ int tess_diagram_create(tess_diagram** out, int real_type, int device) {
 void tess_diagram_destroy(tess_diagram* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    for (DevBuf* b : {&d->xyz, &d->groups, &d->ids, &d->counts, &d->delim, &d->cell_of, &d->rank_in_cell, &d->tmp_idx, &d->sorted, &d->sorted_idx, &d->slot_of,
+    for (DevBuf* b : {&d->xyz, &d->groups, &d->ids, &d->counts, &d->delim, &d->cell_of, &d->rank_in_cell, &d->tmp_idx, &d->arrived, &d->sorted, &d->sorted_idx,
                       &d->groups_sorted, &d->scan_tmp, &d->small})
         b->release();
     for (auto& kv : d->tables) kv.second.dev.release();
@@ -416,10 +416,10 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
     d->delim.reserve(sizeof(uint32_t) * (ncl + 1));
     d->cell_of.reserve(sizeof(uint32_t) * (n + 2));
     d->rank_in_cell.reserve(sizeof(uint32_t) * (n + 2));
-    d->tmp_idx.reserve(sizeof(uint32_t) * n);
+    if (d->has_ids) d->tmp_idx.reserve(sizeof(uint32_t) * n);
+    d->arrived.reserve(sizeof(Particle) * n);
     d->sorted.reserve(sizeof(Particle) * n);
     d->sorted_idx.reserve(sizeof(uint32_t) * n);
-    d->slot_of.reserve(sizeof(uint32_t) * n);
     if (d->has_groups) d->groups_sorted.reserve(sizeof(uint64_t) * n);
     d->scan_tmp.reserve(scan_tmp_bytes(ncl + 1));
     tr.mark("bounds+reserve");
@@ -442,10 +442,10 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
     // K3: delimiters = exclusive scan of the counts (celery.rs:372-414); delim[ncl] = n
     launch_exclusive_scan_u32(d->counts.as<uint32_t>(), d->delim.as<uint32_t>(), ncl + 1, d->scan_tmp.p, d->scan_tmp.bytes, s);
     // K4: counting-sort scatter, canonical in-cell order, gather of the particle records
-    launch_scatter(d->cell_of.as<uint32_t>(), d->rank_in_cell.as<uint32_t>(), d->delim.as<uint32_t>(), d->tmp_idx.as<uint32_t>(), n, s);
-    launch_rank_fix_gather(d->tmp_idx.as<uint32_t>(), d->cell_of.as<uint32_t>(), d->delim.as<uint32_t>(), d->xyz.as<double>(), d->has_ids ? d->ids.as<int64_t>() : nullptr,
-                           d->has_groups ? d->groups.as<uint64_t>() : nullptr, d->sorted.as<Particle>(), d->sorted_idx.as<uint32_t>(), d->slot_of.as<uint32_t>(),
-                           d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr, n, s);
+    launch_scatter_records(d->xyz.as<double>(), d->has_ids ? d->ids.as<int64_t>() : nullptr, d->cell_of.as<uint32_t>(), d->rank_in_cell.as<uint32_t>(), d->delim.as<uint32_t>(),
+                           d->arrived.as<Particle>(), d->has_ids ? d->tmp_idx.as<uint32_t>() : nullptr, n, s);
+    launch_rank_fix(d->arrived.as<Particle>(), d->has_ids ? d->tmp_idx.as<uint32_t>() : nullptr, g, d->delim.as<uint32_t>(), d->has_groups ? d->groups.as<uint64_t>() : nullptr,
+                    d->sorted.as<Particle>(), d->sorted_idx.as<uint32_t>(), d->has_groups ? d->groups_sorted.as<uint64_t>() : nullptr, n, s);
     TESS_CUDA_CHECK(cudaEventRecord(d->ev_bin1, s));
     tr.mark("binning kernels");
     if (slab) {

@@ -140,7 +140,7 @@ struct SmemMask {
 // A staged tile with at least this many candidates waiting is screened candidate-parallel before the planes
 // are offered one by one (0 disables the screen); see the comment at its use.
 #ifndef TESS_PREFILTER_MIN
-#define TESS_PREFILTER_MIN 8
+#define TESS_PREFILTER_MIN 6
 #endif
 struct SmallCfg {
     static constexpr int MINB = TESS_CLIP_MINBLOCKS;
@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 // it is offered, so the one-plane-at-a-time classification is skipped for it (it still counts
                 // as tested).  Dense tiles of clustered inputs lose most of their non-cutting planes here.
                 uint32_t nocut = 0;
-                if (TESS_PREFILTER_MIN > 0 && !radius_mode && __popc(pending) >= TESS_PREFILTER_MIN) {
+                if (TESS_PREFILTER_MIN > 0 && !radius_mode && (t0 | base) != 0u && __popc(pending) >= TESS_PREFILTER_MIN) {
                     const double mar = mul(1e-9, __dsqrt_rn(stop_thr));
                     bool clear_of_all = false;
                     if (((pending >> lane) & 1u) && !src_marker) {
@@ -1150,6 +1150,9 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                         }
                     }
                     nocut = __ballot_sync(FULL, clear_of_all);
+                    // without work counters the screened-out planes simply leave the queue; with them each is
+                    // still counted when its turn comes (tested, all vertices classified), as the oracle counts it
+                    if (!COUNT) pending &= ~nocut;
                 }
                 while (pending) {
                     const int l = __ffs(pending) - 1;
@@ -1158,14 +1161,12 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                         status |= ST_HALO_INSUFFICIENT;
                         continue;
                     }
-                    if ((nocut >> l) & 1u) {  // screened out above: tested, every vertex classified Inside, no cut
-                        if (COUNT) {
-                            c_test += 1;
+                    if (COUNT && ((nocut >> l) & 1u)) {  // screened out above: tested, every vertex classified Inside, no cut
+                        c_test += 1;
 #pragma unroll
-                            for (int p = 0; p < MeshT::NWV; ++p) {
-                                if (p >= M.nwv()) break;
-                                c_vc += __popc(M.vlive.word(p));
-                            }
+                        for (int p = 0; p < MeshT::NWV; ++p) {
+                            if (p >= M.nwv()) break;
+                            c_vc += __popc(M.vlive.word(p));
                         }
                         continue;
                     }

@@ -3,7 +3,7 @@
 //   K1 bounds_reduce        CeleryBounds::new            celery.rs:81-125
 //   K2 cell_histogram       get_cells / get_cell         celery.rs:269-354  (+ per-cell counts)
 //   K3 exclusive_scan       get_delimiters               celery.rs:372-414  (CSR offsets)
-//   K4 scatter + rank_fix   get_sorted_indices           celery.rs:357-369  (counting sort instead
+//   K4 scatter_records + rank_fix   get_sorted_indices   celery.rs:357-369  (counting sort instead
 //                           of sort_unstable_by; order inside a grid cell = ascending particle
 //                           index, the canonical choice where the reference leaves it unspecified)
 //
@@ -234,46 +234,50 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const uint32_t* __restri
 }
 
 // ---------------------------------------------------------------- K4 -----------------------
-__global__ void __launch_bounds__(kThreads) scatter_kernel(const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank_in_cell,
-                                                           const uint32_t* __restrict__ delim, uint32_t* __restrict__ tmp_idx, size_t n) {
+// Counting-sort scatter.  One thread per particle, in input order (coalesced reads): the whole 32-byte
+// record {x, y, z, id} goes to the particle's ARRIVAL slot of its grid cell — one full DRAM sector per
+// particle, where scattering a 4-byte index would dirty the same sector and leave a 24-byte gather of
+// the position for later.
+__global__ void __launch_bounds__(kThreads) scatter_records_kernel(const double* __restrict__ xyz, const int64_t* __restrict__ ids,
+                                                                   const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank_in_cell,
+                                                                   const uint32_t* __restrict__ delim, Particle* __restrict__ arrived,
+                                                                   uint32_t* __restrict__ arrived_idx, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    tmp_idx[__ldg(delim + cell_of[i]) + rank_in_cell[i]] = (uint32_t)i;
+    const uint32_t dst = __ldg(delim + cell_of[i]) + rank_in_cell[i];
+    const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    const int64_t id = ids ? ids[i] : (int64_t)i;
+    double2* o = reinterpret_cast<double2*>(arrived + dst);
+    o[0] = make_double2(x, y);
+    o[1] = make_double2(z, __longlong_as_double(id));
+    if (ids) arrived_idx[dst] = (uint32_t)i;  // insertion index != id only when ids are explicit (slab diagrams)
 }
 
-// Arrival order inside a grid cell depends on atomic timing.  Re-rank each cell's few members by
-// particle index so that the sorted arrays are deterministic, then gather the particle records.
-__global__ void __launch_bounds__(kThreads) rank_fix_gather_kernel(const uint32_t* __restrict__ tmp_idx, const uint32_t* __restrict__ cell_of,
-                                                                   const uint32_t* __restrict__ delim, const double* __restrict__ xyz,
-                                                                   const int64_t* __restrict__ ids, const uint64_t* __restrict__ groups,
-                                                                   Particle* __restrict__ sorted, uint32_t* __restrict__ sorted_idx,
-                                                                   uint32_t* __restrict__ slot_of, uint64_t* __restrict__ groups_sorted, size_t n) {
+// Arrival order inside a grid cell depends on atomic timing.  One thread per arrival slot re-ranks its
+// record among the few members of its cell by user-visible id — the canonical in-cell order (== insertion
+// order when ids are implicit), which also makes a slab-sharded run order candidates exactly like the
+// single-GPU run — and writes it to its final slot.  The cell is recomputed from the position (same
+// function, same operands as K2), so nothing is gathered: reads and writes are sequential in slot order.
+__global__ void __launch_bounds__(kThreads) rank_fix_kernel(const Particle* __restrict__ arrived, const uint32_t* __restrict__ arrived_idx, GridSpec g,
+                                                            const uint32_t* __restrict__ delim, const uint64_t* __restrict__ groups,
+                                                            Particle* __restrict__ sorted, uint32_t* __restrict__ sorted_idx,
+                                                            uint64_t* __restrict__ groups_sorted, size_t n) {
     const size_t s = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const uint32_t i = tmp_idx[s];
-    const uint32_t c = cell_of[i];
+    const double2* q = reinterpret_cast<const double2*>(arrived + s);
+    const double2 a = q[0], b = q[1];
+    const int64_t my = __double_as_longlong(b.y);
+    bool oob;
+    const uint32_t c = local_cell(a.x, a.y, b.x, g, oob);
     const uint32_t d0 = __ldg(delim + c), d1 = __ldg(delim + c + 1);
-    // canonical in-cell order: ascending user-visible id (== insertion index when ids are implicit),
-    // so that a slab-sharded run orders candidates exactly like the single-GPU run
     uint32_t r = 0;
-    if (ids) {
-        const int64_t my = ids[i];
-        for (uint32_t t = d0; t < d1; ++t) r += (ids[tmp_idx[t]] < my) ? 1u : 0u;
-    } else {
-        for (uint32_t t = d0; t < d1; ++t) r += (tmp_idx[t] < i) ? 1u : 0u;
-    }
+    for (uint32_t t = d0; t < d1; ++t) r += (arrived[t].id < my) ? 1u : 0u;
     const uint32_t dst = d0 + r;
-    Particle p;
-    p.x = xyz[3 * (size_t)i];
-    p.y = xyz[3 * (size_t)i + 1];
-    p.z = xyz[3 * (size_t)i + 2];
-    p.id = ids ? ids[i] : (int64_t)i;
-    // one 32-byte sector per record: two 16-byte stores
     double2* o = reinterpret_cast<double2*>(sorted + dst);
-    o[0] = make_double2(p.x, p.y);
-    o[1] = make_double2(p.z, __longlong_as_double(p.id));
+    o[0] = a;
+    o[1] = b;
+    const uint32_t i = arrived_idx ? arrived_idx[s] : (uint32_t)my;
     sorted_idx[dst] = i;
-    slot_of[i] = dst;
     if (groups_sorted) groups_sorted[dst] = groups ? groups[i] : 0ull;
 }
 
@@ -379,17 +383,18 @@ void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t 
     launch_scan_impl<unsigned long long>(in, reinterpret_cast<unsigned long long*>(out), n, tmp, tmp_bytes, s);
 }
 
-void launch_scatter(const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, uint32_t* tmp_idx, size_t n, cudaStream_t s) {
+void launch_scatter_records(const double* xyz, const int64_t* ids, const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, Particle* arrived,
+                            uint32_t* arrived_idx, size_t n, cudaStream_t s) {
     if (!n) return;
-    scatter_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(cell_of, rank_in_cell, delim, tmp_idx, n);
+    scatter_records_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, ids, cell_of, rank_in_cell, delim, arrived, arrived_idx, n);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_rank_fix_gather(const uint32_t* tmp_idx, const uint32_t* cell_of, const uint32_t* delim, const double* xyz, const int64_t* ids, const uint64_t* groups,
-                            Particle* sorted, uint32_t* sorted_idx, uint32_t* slot_of, uint64_t* groups_sorted, size_t n, cudaStream_t s) {
+void launch_rank_fix(const Particle* arrived, const uint32_t* arrived_idx, const GridSpec& g, const uint32_t* delim, const uint64_t* groups, Particle* sorted,
+                     uint32_t* sorted_idx, uint64_t* groups_sorted, size_t n, cudaStream_t s) {
     if (!n) return;
-    rank_fix_gather_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(tmp_idx, cell_of, delim, xyz, ids, groups, sorted, sorted_idx, slot_of, groups_sorted, n);
+    rank_fix_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(arrived, arrived_idx, g, delim, groups, sorted, sorted_idx, groups_sorted, n);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
