@@ -43,7 +43,12 @@ WORKLOADS = {
     "bcc100m": (99_672_064, 5, "bcc"),
 }
 # algorithmic HBM bytes: binning per point, clip per cell
-BYTES_PER_POINT_BINNING = 24 + (24 + 8) + 2 * 4 * 0.81 + (8 + 4 + 4) + (4 + 4 + 8 + 24 + 32 + 8)
+# K2-K4 are what the library's events bracket (K1, the bounds pass, runs before them).  Algorithmic bytes per point
+# (SURVEY.md §8d): K2 read xyz 24 + write cell 4, K3 read+write 4 B per grid cell (0.81 cells per point),
+# K4 read xyz 24 + cell 4, write the sorted position 24 + id 4  =>  90.5.  As implemented (two passes over
+# 32-byte records, a rank per point, 8-byte ids): K2 24+8, K3 6.5, scatter_records 24+8+4+32, rank_fix 32+6.5+32+4.
+BYTES_PER_POINT_BINNING = (24 + 4) + 2 * 4 * 0.81 + (24 + 4 + 24 + 4)
+BYTES_PER_POINT_BINNING_IMPL = (24 + 8) + 2 * 4 * 0.81 + (24 + 8 + 4 + 32) + (32 + 2 * 4 * 0.81 + 32 + 4)
 OUT_MASK = 1 | 2 | 4  # volume | neighbours | areas
 
 
@@ -425,8 +430,10 @@ def main():
     bin_avg = float(np.mean(bin_ms))
     n_binned = (state["res"].n_received if world > 1 else n_local)
     bin_ach = BYTES_PER_POINT_BINNING * n_binned / (bin_avg * 1e-3) / 1e9
-    roofline_binning = {"kernels": "cell_histogram+scan+scatter+rank_fix_gather", "bound": "hbm", "achieved": bin_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": bin_ach / peaks["hbm_gbs"], "avg_ms": bin_avg, "bytes_per_point": BYTES_PER_POINT_BINNING, "share_of_step": bin_avg / ms_per_step}
+    roofline_binning = {"kernels": "cell_histogram+scan+scatter_records+rank_fix", "bound": "hbm", "achieved": bin_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": bin_ach / peaks["hbm_gbs"], "avg_ms": bin_avg, "bytes_per_point": BYTES_PER_POINT_BINNING, "share_of_step": bin_avg / ms_per_step,
+                        "implemented_bytes_per_point": BYTES_PER_POINT_BINNING_IMPL,
+                        "implemented_gbs": BYTES_PER_POINT_BINNING_IMPL * n_binned / (bin_avg * 1e-3) / 1e9}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

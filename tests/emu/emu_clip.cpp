@@ -134,7 +134,7 @@ int emu_clip_run(emu_clip_args* a) {
     g_blocks = a->blocks ? a->blocks : g_os_threads;
     g_reverse = a->reverse != 0;
     g_collectives = 0;
-    launch_clip(P, a->large != 0, nullptr);
+    launch_clip(P, a->large, nullptr);  // 0 small, 1 medium, 2 large (tess::CLIP_*)
     if (a->counters)
         for (int i = 0; i < CNT_N; ++i) a->counters[i] = counters[i];
     a->collectives = g_collectives;
@@ -151,4 +151,5 @@ const unsigned long long* emu_line_hist() { return g_hist; }
 
 uint32_t emu_small_fmax() { return tess::clip_small_fmax(); }
 uint32_t emu_large_fmax() { return tess::clip_large_fmax(); }
+uint32_t emu_medium_fmax() { return tess::clip_medium_fmax(); }
 }

@@ -39,6 +39,7 @@ def lib():
         _lib.emu_clip_run.argtypes = [C.POINTER(Args)]
         _lib.emu_small_fmax.restype = C.c_uint32
         _lib.emu_large_fmax.restype = C.c_uint32
+        _lib.emu_medium_fmax.restype = C.c_uint32
     return _lib
 
 
@@ -96,8 +97,9 @@ class EmuGrid:
              query_xyz=None, want_vertices=False, count=True):
         """count=False runs the instantiation without work counters (the one the product times)."""
         L = lib()
+        tier = {False: 0, True: 2, "medium": 1}[large]  # tess::CLIP_SMALL / CLIP_LARGE / CLIP_MEDIUM
         if fstride is None:
-            fstride = int(L.emu_large_fmax()) if large else 40
+            fstride = (40, int(L.emu_medium_fmax()), int(L.emu_large_fmax()))[tier]
         ws = None if work_slots is None else np.ascontiguousarray(work_slots, np.uint32)
         m = self.n if ws is None else ws.size
         q = None
@@ -116,13 +118,13 @@ class EmuGrid:
         a.work_slots, a.n_work, a.query_xyz = (None if ws is None else ws.ctypes.data), m, (None if q is None else q.ctypes.data)
         geo = None
         if want_vertices:
-            vmax = 1024 if large else 64
+            vmax = (64, 256, 1024)[tier]
             geo = dict(gv=np.zeros((m * vmax, 3)), gl=np.zeros(m * 3 * vmax, np.uint32), cur=np.zeros(2, np.uint64), nv=np.zeros(m, np.uint32),
                        nl=np.zeros(m, np.uint32), vb=np.zeros(m, np.uint64), lb=np.zeros(m, np.uint64), fl=np.zeros(m * fstride, np.uint16))
             a.gv_xyz, a.gl_idx, a.gv_cap, a.gl_cap = geo["gv"].ctypes.data, geo["gl"].ctypes.data, m * vmax, m * 3 * vmax
             a.g_cursor, a.nverts, a.nloops = geo["cur"].ctypes.data, geo["nv"].ctypes.data, geo["nl"].ctypes.data
             a.vbase, a.lbase, a.st_flen = geo["vb"].ctypes.data, geo["lb"].ctypes.data, geo["fl"].ctypes.data
-        a.target_group, a.search_radius, a.flags, a.large, a.fstride = target_group, search_radius, flags, int(large), fstride
+        a.target_group, a.search_radius, a.flags, a.large, a.fstride = target_group, search_radius, flags, tier, fstride
         a.vol, a.nfaces, a.status, a.cell_id = vol.ctypes.data, nfaces.ctypes.data, status.ctypes.data, cell_id.ctypes.data
         a.st_nbr, a.st_area, a.counters = st_nbr.ctypes.data, st_area.ctypes.data, (counters.ctypes.data if count else None)
         a.failed_slots, a.n_failed = failed.ctypes.data, n_failed.ctypes.data

@@ -113,9 +113,27 @@ def test_large_configuration(eb, gen, reverse):
     rl = g.oracle_cells(slots=slots)
     assert max(np.diff(rl.face_offsets)) > 64
     _check(el, rl, "large pass")
-    # and the large configuration on ordinary cells
+    # the medium configuration (256 vertices / 128 faces) cannot hold the centre cell either, but holds the rest
+    em = g.clip(work_slots=slots, large="medium", reverse=reverse)
+    assert (em.status & 0x4).any()
+    _check(em, rl, "medium pass", expect_all=False)
+    # and both on ordinary cells
     some = np.arange(0, g.n, 7, dtype=np.uint32)
     _check(g.clip(work_slots=some, large=True, reverse=reverse), g.oracle_cells(slots=some), "large on ordinary cells")
+    _check(g.clip(work_slots=some, large="medium", reverse=reverse), g.oracle_cells(slots=some), "medium on ordinary cells")
+
+
+def test_medium_configuration_on_cluster_rims(eb, gen):
+    """Cells of a clustered set that overflow the small tables on the way (not in the end) are finished by MediumCfg."""
+    pts = gen.clustered(30000, 4)
+    g = eb.EmuGrid(pts, BOX)
+    e = g.clip()
+    slots = np.sort(e.failed_slots)
+    assert len(slots) > 20
+    em = g.clip(work_slots=slots, large="medium")
+    rm = g.oracle_cells(slots=slots)
+    ok = _check(em, rm, "medium", expect_all=False)
+    assert ok.mean() > 0.9
 
 
 def test_reference_radius_and_group_modes(eb, gen, ob):
@@ -132,7 +150,7 @@ def test_reference_radius_and_group_modes(eb, gen, ob):
         _check(g.clip(target_group=tg), g.oracle_cells(target_group=tg), f"group {tg}")
 
 
-@pytest.mark.parametrize("large", [False, True])
+@pytest.mark.parametrize("large", [False, "medium", True])
 def test_vertex_lists_and_face_loops(eb, gen, large):
     """TESS_OUT_VERTICES: per-face ordered vertex loops bit-identical to
     Polyhedron::compute_face_vertices; the cell's vertex list is the same set of points."""

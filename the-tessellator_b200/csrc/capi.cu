@@ -640,7 +640,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     if (want_vtx) TESS_CUDA_CHECK(cudaMemsetAsync(nloops, 0, sizeof(uint32_t) * n_rows, s));
     int64_t* st_nbr = tmp.get<int64_t>(n_rows * fstride);
     double* st_area = want_area ? tmp.get<double>(n_rows * fstride) : nullptr;
-    uint32_t* ctrl = tmp.get<uint32_t>(16);  // [0] work counter, [1] n_failed, [2]/[3] n_failed of the redo passes, [5] table-only failures
+    uint32_t* ctrl = tmp.get<uint32_t>(16);  // [0] work counter, [1] n_failed, [2] n_failed of redo pass A, [5] table-only failures, [8]/[9] n_failed of the medium/large passes, [12]/[13] their table-only failures
     uint32_t* failed = tmp.get<uint32_t>(n_rows);
     double* query_dev = nullptr;
     if (query) {
@@ -760,7 +760,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.n_work = (uint32_t)(r1 - r0);
         }
         TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c], s));
-        launch_clip(Q, /*large=*/false, s);
+        launch_clip(Q, CLIP_SMALL, s);
         TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c + 1], s));
         // failures so far: [0] all, [1] those that only ran out of search table
         TESS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(E.pinned + 4 * c), ctrl + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -770,17 +770,18 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
 
     // ---- redo passes for `count` failed cells (sorted slots at failed_list):
     //   A: the same small-cell kernel with a wider search table (cells in voids only ran out of table);
-    //   B: what still fails (more than 64 vertices / 40 faces) goes to the large-cell configuration,
-    //      with tables of doubled radius until every walk terminates.
+    //   B: what still fails (more than 64 vertices / 40 faces at some point) goes to the medium configuration
+    //      (256 vertices / 128 faces), with tables of doubled radius while cells run out of table;
+    //   C: what outgrows that too goes to the large configuration (1024 vertices / 512 faces), likewise.
     struct Redo {
-        uint32_t n_a = 0, n_b = 0;
-        const uint32_t *list_a = nullptr, *list_b = nullptr;
-        int64_t *sa_nbr = nullptr, *lg_nbr = nullptr;
-        double *sa_area = nullptr, *lg_area = nullptr;
-        uint16_t *sa_flen = nullptr, *lg_flen = nullptr;
+        uint32_t n_a = 0, n_b = 0, n_c = 0;
+        const uint32_t *list_a = nullptr, *list_b = nullptr, *list_c = nullptr;
+        int64_t *sa_nbr = nullptr, *md_nbr = nullptr, *lg_nbr = nullptr;
+        double *sa_area = nullptr, *md_area = nullptr, *lg_area = nullptr;
+        uint16_t *sa_flen = nullptr, *md_flen = nullptr, *lg_flen = nullptr;
     };
-    const uint32_t lstride = clip_large_fmax();
-    uint32_t total_redo_a = 0, total_redo_b = 0;
+    const uint32_t mstride = clip_medium_fmax(), lstride = clip_large_fmax();
+    uint32_t total_redo_a = 0, total_redo_b = 0, total_redo_c = 0;
     int final_R = 0;
     auto redo = [&](uint32_t* failed_list, uint32_t count, uint32_t table_only, Redo& ro) -> int {
         const int cpd_m1 = std::max(static_cast<int>(d->grid.cpd) - 1, 1);
@@ -809,50 +810,74 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.failed_cap = count;
             Q.mark_large = 1;
             TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 2, 0, sizeof(uint32_t), s));
-            launch_clip(Q, /*large=*/false, s);
+            launch_clip(Q, CLIP_SMALL, s);
             TESS_CUDA_CHECK(cudaMemcpyAsync(&ro.n_b, ctrl + 2, sizeof(ro.n_b), cudaMemcpyDeviceToHost, s));
             TESS_CUDA_CHECK(cudaStreamSynchronize(s));
         }
         ro.list_b = list_b;
-        if (ro.n_b > 0) {
-            if (ro.n_b > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
-            ro.lg_nbr = tmp.get<int64_t>((size_t)ro.n_b * lstride);
-            ro.lg_area = want_area ? tmp.get<double>((size_t)ro.n_b * lstride) : nullptr;
-            ro.lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)ro.n_b * lstride) : nullptr;
-            uint32_t* failed_c = tmp.get<uint32_t>(ro.n_b);
-            unsigned long long* redo_counters = tmp.get<unsigned long long>(CNT_N);
+        // one tier over `n` listed cells: widen the table while some cell only ran out of table; the cells that
+        // still fail afterwards (capacity) are left in failed_out
+        unsigned long long* redo_counters = nullptr;
+        auto run_tier = [&](int tier, const uint32_t* list, uint32_t n, uint32_t stride, int64_t* st_n, double* st_a, uint16_t* st_f, uint32_t* failed_out,
+                            uint32_t* still_out) {
+            uint32_t* nf = ctrl + (tier == CLIP_MEDIUM ? 8 : 9);
+            uint32_t still = 0;
             for (int attempt = 0; attempt < 12; ++attempt) {
                 const ShellTable& t2 = d->table(R, s);
                 ClipParams Q = P;
                 Q.table = t2.dev.as<ShellEntry>();
                 Q.table_len = t2.len;
                 Q.table_full = t2.full ? 1u : 0u;
-                Q.n_work = ro.n_b;
-                Q.work_slots = list_b;
-                Q.st_nbr = ro.lg_nbr; Q.st_area = ro.lg_area; Q.st_flen = ro.lg_flen; Q.fstride = lstride; Q.stage_by_work = 1;
+                Q.n_work = n;
+                Q.work_slots = list;
+                Q.st_nbr = st_n; Q.st_area = st_a; Q.st_flen = st_f; Q.fstride = stride; Q.stage_by_work = 1;
                 Q.counters = want_cnt ? redo_counters : nullptr;  // only the last attempt's counts are kept
                 if (want_cnt) TESS_CUDA_CHECK(cudaMemsetAsync(redo_counters, 0, sizeof(unsigned long long) * CNT_N, s));
-                Q.failed_slots = failed_c;
-                Q.n_failed = ctrl + 3;
-                Q.failed_cap = ro.n_b;
+                Q.failed_slots = failed_out;
+                Q.n_failed = nf;
+                Q.failed_cap = n;
                 Q.mark_large = 1;
-                TESS_CUDA_CHECK(cudaMemsetAsync(ctrl + 3, 0, sizeof(uint32_t), s));
-                launch_clip(Q, /*large=*/true, s);
-                uint32_t still = 0;
-                TESS_CUDA_CHECK(cudaMemcpyAsync(&still, ctrl + 3, sizeof(still), cudaMemcpyDeviceToHost, s));
+                TESS_CUDA_CHECK(cudaMemsetAsync(nf, 0, sizeof(uint32_t), s));
+                TESS_CUDA_CHECK(cudaMemsetAsync(nf + 4, 0, sizeof(uint32_t), s));
+                launch_clip(Q, tier, s);
+                uint32_t h[5] = {0, 0, 0, 0, 0};
+                TESS_CUDA_CHECK(cudaMemcpyAsync(h, nf, sizeof(h), cudaMemcpyDeviceToHost, s));
                 TESS_CUDA_CHECK(cudaStreamSynchronize(s));
-                if (still == 0 || t2.full) break;  // remaining failures (if any) are capacity overflows: reported in status
+                still = h[0];
+                if (h[4] == 0 || t2.full) break;  // nobody ran out of table: what still fails needs larger tables of the mesh
                 R = std::min(2 * R, cpd_m1);
             }
-            if (want_cnt) {
+            if (want_cnt) {  // cells this tier finished (the kernel counts only those)
                 unsigned long long h[CNT_N];
                 TESS_CUDA_CHECK(cudaMemcpyAsync(h, redo_counters, sizeof(h), cudaMemcpyDeviceToHost, s));
                 TESS_CUDA_CHECK(cudaStreamSynchronize(s));
                 for (int i = 0; i < CNT_N; ++i) r->counters_redo[i] += h[i];
             }
+            *still_out = still;
+        };
+        if (ro.n_b > 0) {
+            if (ro.n_b > (1u << 22)) return fail(TESS_ERR_CAPACITY, "more than 2^22 cells need the medium-cell path");
+            if (want_cnt) redo_counters = tmp.get<unsigned long long>(CNT_N);
+            ro.md_nbr = tmp.get<int64_t>((size_t)ro.n_b * mstride);
+            ro.md_area = want_area ? tmp.get<double>((size_t)ro.n_b * mstride) : nullptr;
+            ro.md_flen = want_vtx ? tmp.get<uint16_t>((size_t)ro.n_b * mstride) : nullptr;
+            uint32_t* list_c = tmp.get<uint32_t>(ro.n_b);
+            run_tier(CLIP_MEDIUM, list_b, ro.n_b, mstride, ro.md_nbr, ro.md_area, ro.md_flen, list_c, &ro.n_c);
+            ro.list_c = list_c;
+        }
+        if (ro.n_c > 0) {
+            if (ro.n_c > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
+            // the kernel appends failed cells in completion order; the large pass wants its work list sorted like every list
+            ro.lg_nbr = tmp.get<int64_t>((size_t)ro.n_c * lstride);
+            ro.lg_area = want_area ? tmp.get<double>((size_t)ro.n_c * lstride) : nullptr;
+            ro.lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)ro.n_c * lstride) : nullptr;
+            uint32_t* failed_d = tmp.get<uint32_t>(ro.n_c);
+            uint32_t still = 0;
+            run_tier(CLIP_LARGE, ro.list_c, ro.n_c, lstride, ro.lg_nbr, ro.lg_area, ro.lg_flen, failed_d, &still);  // what still fails is reported in status
         }
         total_redo_a += ro.n_a;
         total_redo_b += ro.n_b;
+        total_redo_c += ro.n_c;
         final_R = std::max(final_R, R);
         return TESS_OK;
     };
@@ -894,8 +919,10 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
                              fstride, r1 - r0, r->nbr, r->area, flen_csr, s);
         if (ro.n_a)  // pass A rows (rows redone again by pass B are overwritten right after)
             launch_compact_redo(ro.list_a, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.sa_nbr, ro.sa_area, ro.sa_flen, fstride, ro.n_a, r->nbr, r->area, flen_csr, s);
-        if (ro.n_b)
-            launch_compact_redo(ro.list_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.lg_nbr, ro.lg_area, ro.lg_flen, lstride, ro.n_b, r->nbr, r->area, flen_csr, s);
+        if (ro.n_b)  // (likewise for rows redone by pass C)
+            launch_compact_redo(ro.list_b, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.md_nbr, ro.md_area, ro.md_flen, mstride, ro.n_b, r->nbr, r->area, flen_csr, s);
+        if (ro.n_c)
+            launch_compact_redo(ro.list_c, P.row_of_slot, P.row_base, r->nfaces, r->offsets, ro.lg_nbr, ro.lg_area, ro.lg_flen, lstride, ro.n_c, r->nbr, r->area, flen_csr, s);
         launch_clear_status_bits(r->status + r0, r1 - r0, ST_LARGE_PATH, s);  // internal marker of the redo passes
         if (streaming) {
             // the packed chunk goes to the host while the next chunks are clipped
@@ -929,7 +956,8 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     }
     r->n_faces = total;
     if (std::getenv("TESS_TRACE") && (total_redo_a || total_redo_b))
-        std::fprintf(stderr, "[tess trace] redo: pass A (wider table) re-ran %u cells, pass B (large cells, final R=%d) %u\n", total_redo_a, final_R, total_redo_b);
+        std::fprintf(stderr, "[tess trace] redo: pass A (wider table) re-ran %u cells, pass B (medium cells) %u, pass C (large cells) %u, final R=%d\n", total_redo_a, total_redo_b,
+                     total_redo_c, final_R);
     tr.mark("clip + redo + pack");
 
     if (want_vtx) {

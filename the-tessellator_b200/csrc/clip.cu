@@ -153,6 +153,20 @@ struct SmallCfg {
     static constexpr uint32_t NONE = 0xFFu;
     static constexpr int SHIFT = 8;
 };
+// Cells that outgrow the small tables at some point of their construction — mostly cells at the rim of a
+// dense cluster, cut by hundreds of planes in arrival order before they shrink to 15-25 faces — fit this
+// middle configuration, which keeps ~10 warps per SM resident where the large one keeps 2.
+struct MediumCfg {
+    static constexpr int MINB = 5;
+    static constexpr int VMAX = 256, EMAX = 768, FMAX = 128;
+    static constexpr int E_LIMIT = 768;
+    static constexpr int WARPS = 2;
+    static constexpr bool REG = false;
+    using Idx = uint16_t;
+    using EdgeWord = unsigned long long;
+    static constexpr uint32_t NONE = 0xFFFFu;
+    static constexpr int SHIFT = 16;
+};
 struct LargeCfg {
     static constexpr int MINB = 1;
     static constexpr int VMAX = 1024, EMAX = 3072, FMAX = 512;
@@ -410,20 +424,19 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
             __syncwarp();
             // successor: the crossing of the face my re-entering half-edge's flip lies in
             if (act) ks = sm->kof[fs] & 31u;
-            const bool s_act = __shfl_sync(FULL, act, (int)ks);
-            const uint32_t s_f = __shfl_sync(FULL, f, (int)ks);
-            const bool ok1 = !act || (s_act && s_f == fs);
+            // one shuffle: an inactive lane answers with a face id nobody has
+            const uint32_t s_f = __shfl_sync(FULL, act ? f : 0xFFFFu, (int)ks);
+            const bool ok1 = !act || s_f == fs;
             if (act && ok1) sm->pred[ks] = (Idx)lane;
-            if (!__all_sync(FULL, ok1)) return CUT_FALLBACK;
             __syncwarp();
             // predecessor; succ is a bijection of the crossings iff every crossing is its predecessor's successor
             if (act) pk = (uint32_t)sm->pred[lane] & 31u;
-            const bool p_act = __shfl_sync(FULL, act, (int)pk);
-            const uint32_t p_ks = __shfl_sync(FULL, ks, (int)pk);
-            o = __shfl_sync(FULL, so, (int)pk);
-            fo = __shfl_sync(FULL, r, (int)pk);
-            if (!act) fo = 0xFFFFu;
-            if (!__all_sync(FULL, !act || (p_act && p_ks == (uint32_t)lane))) return CUT_FALLBACK;
+            // one shuffle: {successor (0xFF from an inactive lane), flip of the re-entering half-edge, the half-edge}
+            const uint32_t from_pred = __shfl_sync(FULL, (act ? ks : 0xFFu) | (so << 8) | (r << 16), (int)pk);
+            o = (from_pred >> 8) & 0xFFu;
+            fo = act ? (from_pred >> 16) & 0xFFu : 0xFFFFu;
+            // (a lane whose successor was wrong wrote no predecessor entry: whatever the others read there, the vote fails)
+            if (!__all_sync(FULL, ok1 && (!act || (from_pred & 0xFFu) == (uint32_t)lane))) return CUT_FALLBACK;
         }
     } else {
         // 1. sweep the half-edge table for the outgoing half-edges and for what dies
@@ -554,8 +567,15 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         ck = pop_slot(2 * (int)wi);
         br = pop_slot(2 * (int)wi + 1);
     }
-    const uint32_t nv_pred = __shfl_sync(FULL, nv, (int)pk);  // previous_intersection (:550, :600)
-    const uint32_t ck_pred = __shfl_sync(FULL, ck, (int)pk);
+    uint32_t nv_pred, ck_pred;  // previous_intersection (:550, :600) and its cap edge
+    if constexpr (Cfg::REG) {
+        const uint32_t both = __shfl_sync(FULL, nv | (ck << 8), (int)pk);
+        nv_pred = both & 0xFFu;
+        ck_pred = both >> 8;
+    } else {
+        nv_pred = __shfl_sync(FULL, nv, (int)pk);
+        ck_pred = __shfl_sync(FULL, ck, (int)pk);
+    }
     const uint32_t ck0 = __shfl_sync(FULL, ck, (int)k0);
     const uint32_t br_succ = __shfl_sync(FULL, br, (int)ks);
     uint32_t nb_lo = 0, nb_hi = 0;
@@ -1124,6 +1144,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 }
                 __syncwarp();
                 uint32_t pending = __ballot_sync(FULL, cand && !(src_key > stop_thr));
+                const uint32_t marker_lanes = __ballot_sync(FULL, src_marker);
                 // Screen (not in the reference, results unchanged): with many candidates waiting, every lane
                 // first tests ITS plane against all live vertices.  A plane that keeps every vertex of the
                 // current polytope inside by a margin far above any rounding error (1e-9 of the cell's radius;
@@ -1132,7 +1153,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 // it is offered, so the one-plane-at-a-time classification is skipped for it (it still counts
                 // as tested).  Dense tiles of clustered inputs lose most of their non-cutting planes here.
                 uint32_t nocut = 0;
-                if (TESS_PREFILTER_MIN > 0 && !radius_mode && (t0 | base) != 0u && __popc(pending) >= TESS_PREFILTER_MIN) {
+                auto screen = [&]() {
                     const double mar = mul(1e-9, __dsqrt_rn(stop_thr));
                     bool clear_of_all = false;
                     if (((pending >> lane) & 1u) && !src_marker) {
@@ -1149,15 +1170,18 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                             }
                         }
                     }
-                    nocut = __ballot_sync(FULL, clear_of_all);
+                    nocut |= __ballot_sync(FULL, clear_of_all);
                     // without work counters the screened-out planes simply leave the queue; with them each is
                     // still counted when its turn comes (tested, all vertices classified), as the oracle counts it
                     if (!COUNT) pending &= ~nocut;
-                }
+                };
+                // (not the first tile of a cell: it meets the whole container, which nearly every plane cuts, and a
+                // screen half-way through it catches 1-2 planes for the price of one more pass over the vertices)
+                if (TESS_PREFILTER_MIN > 0 && !radius_mode && (t0 | base) != 0u && __popc(pending) >= TESS_PREFILTER_MIN) screen();
                 while (pending) {
                     const int l = __ffs(pending) - 1;
                     pending &= pending - 1;
-                    if (__shfl_sync(FULL, (int)src_marker, l)) {
+                    if ((marker_lanes >> l) & 1u) {
                         status |= ST_HALO_INSUFFICIENT;
                         continue;
                     }
@@ -1439,14 +1463,18 @@ void launch_cfg(const ClipParams& p, cudaStream_t s) {
 
 }  // namespace
 
-void launch_clip(const ClipParams& p, bool large, cudaStream_t s) {
+void launch_clip(const ClipParams& p, int tier, cudaStream_t s) {
     const bool count = p.counters != nullptr;
-    if (large) {
+    if (tier == CLIP_LARGE) {
         if (count) launch_cfg<LargeCfg, true>(p, s); else launch_cfg<LargeCfg, false>(p, s);
+    } else if (tier == CLIP_MEDIUM) {
+        if (count) launch_cfg<MediumCfg, true>(p, s); else launch_cfg<MediumCfg, false>(p, s);
     } else {
         if (count) launch_cfg<SmallCfg, true>(p, s); else launch_cfg<SmallCfg, false>(p, s);
     }
 }
+uint32_t clip_medium_fmax() { return MediumCfg::FMAX; }
+uint32_t clip_medium_vmax() { return MediumCfg::VMAX; }
 uint32_t clip_small_fmax() { return SmallCfg::FMAX; }
 uint32_t clip_small_vmax() { return SmallCfg::VMAX; }
 uint32_t clip_large_fmax() { return LargeCfg::FMAX; }
