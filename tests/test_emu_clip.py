@@ -179,3 +179,18 @@ def test_cells_at_query_points(eb, gen):
         nf = int(e.nfaces[i])
         assert e.neighbors[e.face_offsets[i]: e.face_offsets[i] + nf].tolist() == r.neighbors.tolist()
         assert e.volumes[i] == r.volumes[0] and np.array_equal(e.areas[e.face_offsets[i]: e.face_offsets[i] + nf], r.areas)
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1.0, 1e3])
+def test_other_scales_and_oblong_boxes(eb, gen, scale):
+    """The tolerance of the reference is absolute (1e-12) while the candidate screen's margin is relative to the
+    cell: small, large and strongly anisotropic containers must stay bit-identical, counters included."""
+    pts = gen.uniform(2500, 71) * np.array([scale, 3.0 * scale, 0.25 * scale]) + np.array([5.0 * scale, -scale, 0.0])
+    box = (5.0 * scale, -scale, 0.0, 6.0 * scale, 2.0 * scale, 0.25 * scale)
+    g = eb.EmuGrid(pts, box, table_radius=-1)
+    e = g.clip()
+    r = g.oracle_cells()
+    _check(e, r, f"scale {scale}")
+    for k in ("visited", "tested", "vertex_classifications", "cuts", "new_vertices", "faces"):
+        assert e.counters[k] == r.counters[k], k
+    assert abs(e.volumes.sum() / (0.75 * scale ** 3) - 1.0) < 1e-12

@@ -1033,11 +1033,13 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
     const bool radius_mode = !(P.search_radius != P.search_radius);  // not NaN
     unsigned long long t_vis = 0, t_test = 0, t_vc = 0, t_cuts = 0, t_nv = 0, t_tab = 0, t_deg = 0, t_faces = 0;  // totals of finished cells
 
+    // the next cell is claimed while the current one is built: the atomic's round trip is off the critical path
+    uint32_t claimed = 0;
+    if (lane == 0) claimed = atomicAdd(P.work_counter, 1u);
     for (;;) {
-        uint32_t work = 0;
-        if (lane == 0) work = atomicAdd(P.work_counter, 1u);
-        work = __shfl_sync(FULL, work, 0);
+        const uint32_t work = __shfl_sync(FULL, claimed, 0);
         if (work >= P.n_work) break;
+        if (lane == 0) claimed = atomicAdd(P.work_counter, 1u);
         uint32_t c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0, c_deg = 0;  // this cell
 
         // ---- the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207) -----------
