@@ -244,22 +244,12 @@ __global__ void __launch_bounds__(kThreads) scatter_records_kernel(const double*
                                                                    uint32_t* __restrict__ arrived_idx, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-#ifdef TESS_STREAM_HINTS
-    // everything streams once (evict-first) except the delimiters, which are gathered and should stay in L2
-    const uint32_t dst = __ldg(delim + __ldcs(cell_of + i)) + __ldcs(rank_in_cell + i);
-    const double x = __ldcs(xyz + 3 * i), y = __ldcs(xyz + 3 * i + 1), z = __ldcs(xyz + 3 * i + 2);
-    const int64_t id = ids ? ids[i] : (int64_t)i;
-    double2* o = reinterpret_cast<double2*>(arrived + dst);
-    __stcs(o, make_double2(x, y));
-    __stcs(o + 1, make_double2(z, __longlong_as_double(id)));
-#else
     const uint32_t dst = __ldg(delim + cell_of[i]) + rank_in_cell[i];
     const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     const int64_t id = ids ? ids[i] : (int64_t)i;
     double2* o = reinterpret_cast<double2*>(arrived + dst);
     o[0] = make_double2(x, y);
     o[1] = make_double2(z, __longlong_as_double(id));
-#endif
     if (ids) arrived_idx[dst] = (uint32_t)i;  // insertion index != id only when ids are explicit (slab diagrams)
 }
 
