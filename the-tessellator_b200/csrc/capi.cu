@@ -867,7 +867,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         }
         if (ro.n_c > 0) {
             if (ro.n_c > (1u << 20)) return fail(TESS_ERR_CAPACITY, "more than 2^20 cells need the large-cell path");
-            // the kernel appends failed cells in completion order; the large pass wants its work list sorted like every list
+            // (list_c, like every failed-cell list, is in completion order: rows are found through row_of_slot)
             ro.lg_nbr = tmp.get<int64_t>((size_t)ro.n_c * lstride);
             ro.lg_area = want_area ? tmp.get<double>((size_t)ro.n_c * lstride) : nullptr;
             ro.lg_flen = want_vtx ? tmp.get<uint16_t>((size_t)ro.n_c * lstride) : nullptr;
