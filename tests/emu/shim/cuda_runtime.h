@@ -10,7 +10,12 @@
 #include <atomic>
 #include <cmath>
 
+#include <functional>
+
 #include "../warp_emu.hpp"
+
+// generic kernel launch of the emulated build (TESS_LAUNCH in common.cuh); defined by the harness
+void emu_launch_generic(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body);
 
 #define TESS_WARP_EMU 1
 #define TESS_UNIFORM_BEGIN(ptr, bytes) emu::uniform_begin((ptr), (bytes), __LINE__)
@@ -37,6 +42,13 @@ struct __attribute__((aligned(16))) double2 {
 struct __attribute__((aligned(16))) double4 {
     double x, y, z, w;
 };
+struct __attribute__((aligned(8))) uint2 {
+    unsigned x, y;
+};
+struct __attribute__((aligned(16))) uint4 {
+    unsigned x, y, z, w;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 
@@ -59,6 +71,9 @@ inline double4 make_double4(double x, double y, double z, double w) { return dou
 #define __reduce_add_sync(m, v) emu::reduce_add((m), (unsigned)(v), __LINE__)
 #define __match_any_sync(m, v) emu::match_any((m), (uint64_t)(v), __LINE__)
 #define __syncwarp() emu::syncwarp(__LINE__)
+#define __syncthreads() emu::syncthreads(__LINE__)
+// static shared arrays: one block at a time runs on a host thread
+#define __shared__ static thread_local
 
 // ---- scalar intrinsics ----------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -133,6 +148,19 @@ template <class T>
 inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T>
 inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_RELAXED); }
+template <class T>
+inline T atomicExch(T* p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template <class T>
+inline T min(T a, T b) { return b < a ? b : a; }
+template <class T>
+inline T max(T a, T b) { return a < b ? b : a; }
+// host-side runtime calls the launchers make
+inline cudaError_t cudaMallocAsync(void* pp, size_t bytes, cudaStream_t) { *static_cast<void**>(pp) = malloc(bytes); return cudaSuccess; }
+template <class T>
+inline cudaError_t cudaMallocAsync(T** pp, size_t bytes, cudaStream_t) { *pp = static_cast<T*>(malloc(bytes)); return cudaSuccess; }
+inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t bytes, cudaStream_t) { memset(p, v, bytes); return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 template <class T>
 inline T atomicMax(T* p, T v) {
     T o = __atomic_load_n(p, __ATOMIC_RELAXED);

@@ -2,6 +2,7 @@
 #include "warp_emu.hpp"
 
 #include <atomic>
+#include <functional>
 
 #if !defined(__x86_64__)
 #error "the warp emulator's context switch is written for x86-64"
@@ -81,7 +82,10 @@ static unsigned long long run_block(Block& b, bool reverse) {
             prepare(f);
         }
         W->pre_span = W->post_span = 0;
+        W->deposits = 0;
     }
+    b.bar_count = 0;
+    b.bar_gen = 0;
     b.collectives = 0;
     bool alive = true;
     while (alive) {
@@ -95,10 +99,8 @@ static unsigned long long run_block(Block& b, bool reverse) {
                 emu_switch(&b.sched_sp, f.sp);
                 if (!f.done) alive = true;
             }
-            // all 32 lanes of a warp leave together or not at all
-            unsigned nd = 0;
-            for (unsigned l = 0; l < 32; ++l) nd += W->f[l].done ? 1u : 0u;
-            if (nd != 0 && nd != 32) die("part of a warp left the kernel while the rest waits in a collective", -1, -1);
+            // (lanes of a warp may leave one round apart after a block barrier; a lane that leaves while the others
+            // wait in a collective is caught by the collective's own watchdog)
         }
     }
     tl_block = nullptr;
@@ -144,4 +146,13 @@ LaunchStats launch(void (*entry)(const void*), const void* arg, unsigned nblocks
     return st;
 }
 
+unsigned g_os_threads = 1;
+bool g_reverse = false;
+
 }  // namespace emu
+
+// TESS_LAUNCH of the emulated build (common.cuh)
+void emu_launch_generic(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
+    if (!grid) return;
+    emu::launch([](const void* a) { (*static_cast<const std::function<void()>*>(a))(); }, &body, grid, block, smem, emu::g_os_threads, emu::g_reverse);
+}

@@ -42,6 +42,7 @@ struct Warp {
     uint32_t tag[2][32];
     uint32_t seq[2][32];
     Fiber f[32];
+    unsigned long long deposits = 0;  // lanes that have entered a collective so far (32 per collective)
     std::vector<unsigned char> uni_pre, uni_post;
     uint32_t pre_span = 0, post_span = 0;
 };
@@ -55,6 +56,7 @@ struct Block {
     unsigned bid = 0, nblocks = 0, nthreads = 0;
     unsigned long long collectives = 0;
     unsigned long long* line_hist = nullptr;  // optional: executions of each collective by source line (65536 entries)
+    unsigned bar_count = 0, bar_gen = 0;      // __syncthreads
 };
 extern thread_local Block* tl_block;
 
@@ -125,7 +127,13 @@ inline const uint64_t* rendezvous(uint64_t v, uint32_t tag) {
     w->seq[k][f->lane] = f->ncoll;
     const uint32_t my_seq = f->ncoll++;
     uniform_span_end((int)(tag & 0xFFFFFu));
-    yield_to_scheduler();
+    // wait for all 32 lanes: lanes of a warp may be one scheduling round apart after a block barrier
+    w->deposits++;
+    unsigned long long spins = 0;
+    do {
+        yield_to_scheduler();
+        if (++spins > (1ull << 22)) die("a warp collective never completed (some lane does not reach it)", (int)(tag & 0xFFFFFu), -1);
+    } while (w->deposits < 32ull * ((unsigned long long)my_seq + 1ull));
     uniform_span_start();
     // every lane checks its neighbour: a chain of equalities makes all 32 equal
     const unsigned nb = (f->lane + 1u) & 31u;
@@ -246,6 +254,22 @@ inline unsigned match_any(unsigned mask, uint64_t v, int line) {
 }
 inline void syncwarp(int line) { rendezvous(0, OP_SYNC | (uint32_t)line); }
 
+// __syncthreads(): all threads of the block
+inline void syncthreads(int line) {
+    Block* b = tl_block;
+    const unsigned gen = b->bar_gen;
+    if (++b->bar_count == b->nthreads) {
+        b->bar_count = 0;
+        b->bar_gen++;
+        return;
+    }
+    unsigned long long spins = 0;
+    while (b->bar_gen == gen) {
+        yield_to_scheduler();
+        if (++spins > (1ull << 22)) die("__syncthreads never completed (a thread left the kernel or skipped the barrier)", line, -1);
+    }
+}
+
 // ---- running a grid -------------------------------------------------------------------------
 void fiber_trampoline();
 
@@ -254,6 +278,9 @@ struct LaunchStats {
 };
 // when set (single host thread only), every launch adds its per-source-line collective counts here
 extern unsigned long long* g_line_hist;
+// how TESS_LAUNCH runs a grid: host threads, lane order
+extern unsigned g_os_threads;
+extern bool g_reverse;
 
 // Runs `entry(arg)` as a grid of `nblocks` CTAs of `nthreads` threads; CTAs are spread over
 // `os_threads` host threads.  `reverse`: lanes of a warp are resumed 31..0 instead of 0..31.

@@ -141,3 +141,81 @@ class EmuGrid:
         """The oracle's cells in the kernel's row order (grid order, or the given sorted slots)."""
         ids = self.sorted_indices if slots is None else self.sorted_indices[np.asarray(slots, np.int64)]
         return self.oracle.compute_cells(ids=ids.astype(np.uint64), **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# grid.cu (binning pass) and query.cu (radius queries) on the emulator
+# ------------------------------------------------------------------------------------------------
+class GridArgs(C.Structure):
+    _fields_ = [
+        ("xyz", C.c_void_p), ("n", C.c_uint32), ("ids", C.c_void_p), ("groups", C.c_void_p), ("bounds", C.c_double * 6), ("cell_info", C.c_double * 6),
+        ("cpd", C.c_uint32), ("local_lo", C.c_uint32), ("local_hi", C.c_uint32), ("bounds_out", C.c_void_p), ("cell_of", C.c_void_p), ("delim", C.c_void_p),
+        ("sorted", C.c_void_p), ("sorted_idx", C.c_void_p), ("groups_sorted", C.c_void_p), ("plane_counts", C.c_void_p), ("oob", C.c_uint32),
+        ("os_threads", C.c_uint32), ("reverse", C.c_uint32),
+    ]
+
+
+class QueryArgs(C.Structure):
+    _fields_ = [
+        ("particles", C.c_void_p), ("n", C.c_uint32), ("delim", C.c_void_p), ("groups_sorted", C.c_void_p), ("table_key", C.c_void_p), ("table_ijk", C.c_void_p),
+        ("table_len", C.c_uint32), ("table_full", C.c_uint32), ("bounds", C.c_double * 6), ("cell_info", C.c_double * 6), ("cpd", C.c_uint32),
+        ("xyz", C.c_void_p), ("n_query", C.c_uint32), ("radius", C.c_double), ("mode", C.c_int32), ("target_group", C.c_int64),
+        ("offsets", C.c_void_p), ("indices", C.c_void_p), ("cap", C.c_uint64), ("flags", C.c_void_p), ("os_threads", C.c_uint32), ("reverse", C.c_uint32),
+    ]
+
+
+_aux = {}
+
+
+def _aux_lib(name):
+    if name not in _aux:
+        subprocess.check_call(["make", "-s", "-C", EMU_DIR, f"libemu_{name}.so"])
+        _aux[name] = C.CDLL(os.path.join(EMU_DIR, f"libemu_{name}.so"))
+    return _aux[name]
+
+
+def binning(points, oracle: "ob.Diagram", ids=None, groups=None, local=None, os_threads=4, reverse=False):
+    """K1-K4 of grid.cu on the emulator, with the grid parameters tess_diagram_initialize would derive
+    (taken from the oracle).  Returns a dict of the arrays the pass produces."""
+    L = _aux_lib("grid")
+    pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    n, cpd = pts.shape[0], oracle.cpd
+    lo, hi = (0, cpd) if local is None else local
+    ncl = (hi - lo) * cpd * cpd
+    out = dict(bounds=np.zeros(6), cell_of=np.zeros(n + 2, np.uint32), delim=np.zeros(ncl + 1, np.uint32), sorted=np.zeros((n, 4)),
+               sorted_idx=np.zeros(n, np.uint32), groups_sorted=np.zeros(n, np.uint64), plane_counts=np.zeros(cpd, np.uint64))
+    a = GridArgs()
+    a.xyz, a.n = pts.ctypes.data, n
+    idv = None if ids is None else np.ascontiguousarray(ids, np.int64)
+    grv = None if groups is None else np.ascontiguousarray(groups, np.uint64)
+    a.ids, a.groups = (None if idv is None else idv.ctypes.data), (None if grv is None else grv.ctypes.data)
+    a.bounds, a.cell_info = (C.c_double * 6)(*oracle.bounds()), (C.c_double * 6)(*oracle.cell_info())
+    a.cpd, a.local_lo, a.local_hi = cpd, lo, hi
+    a.bounds_out, a.cell_of, a.delim, a.sorted = out["bounds"].ctypes.data, out["cell_of"].ctypes.data, out["delim"].ctypes.data, out["sorted"].ctypes.data
+    a.sorted_idx, a.groups_sorted, a.plane_counts = out["sorted_idx"].ctypes.data, (out["groups_sorted"].ctypes.data if grv is not None else None), out["plane_counts"].ctypes.data
+    a.os_threads, a.reverse = os_threads, int(reverse)
+    assert L.emu_grid_run(C.byref(a)) == 0
+    out["cell_of"] = out["cell_of"][:n]
+    out["oob"] = int(a.oob)
+    return out
+
+
+def radius_query(grid: EmuGrid, xyz, radius, mode, target_group=-1, os_threads=4, reverse=False):
+    """query.cu on the emulator: per query the particle ids in the reference's order.  mode 0 cell radius, 1 real radius,
+    2 expand_all_in_radius (search table)."""
+    L = _aux_lib("query")
+    q = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+    m = q.shape[0]
+    cap = max(1, m * grid.n)
+    offsets, indices, flags = np.zeros(m + 1, np.uint64), np.zeros(cap, np.int64), np.zeros(m, np.uint32)
+    a = QueryArgs()
+    a.particles, a.n, a.delim = grid.particles.ctypes.data, grid.n, grid.delim.ctypes.data
+    a.groups_sorted = None if grid.groups_sorted is None else grid.groups_sorted.ctypes.data
+    a.table_key, a.table_ijk, a.table_len, a.table_full = grid.table_key.ctypes.data, grid.table_ijk.ctypes.data, grid.table_key.size, grid.table_full
+    a.bounds, a.cell_info, a.cpd = (C.c_double * 6)(*grid.bounds), (C.c_double * 6)(*grid.cell_info), grid.cpd
+    a.xyz, a.n_query, a.radius, a.mode, a.target_group = q.ctypes.data, m, radius, mode, target_group
+    a.offsets, a.indices, a.cap, a.flags = offsets.ctypes.data, indices.ctypes.data, cap, flags.ctypes.data
+    a.os_threads, a.reverse = os_threads, int(reverse)
+    assert L.emu_query_run(C.byref(a)) == 0
+    o = offsets.astype(np.int64)
+    return [indices[o[i]:o[i + 1]].tolist() for i in range(m)], flags

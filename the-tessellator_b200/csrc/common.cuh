@@ -119,6 +119,15 @@ struct QueryParams {
             throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(e__)); \
     } while (0)
 
+// Kernel launch.  Under TESS_WARP_EMU (tests/emu: the kernel sources compiled by g++ and run lane by lane on the CPU —
+// test infrastructure, never part of the library) the launch goes to the emulator instead.
+#ifdef TESS_WARP_EMU
+#define TESS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu_launch_generic((unsigned)(grid), (unsigned)(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
+#else
+#define TESS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 // every kernel launch of the library is counted (tess_kernel_launch_count)
 void note_launch(int n = 1);
 unsigned long long launch_count();

@@ -344,9 +344,9 @@ void launch_bounds(const double* xyz, size_t n, double* bounds6, cudaStream_t s)
     TESS_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(double) * 6 * kBoundsBlocks, s));
     const size_t npairs = (n + 1) / 2;
     const int nb = (int)std::min<size_t>(kBoundsBlocks, std::max<size_t>(1, (npairs + kThreads - 1) / kThreads));
-    bounds_partial_kernel<<<nb, kThreads, 0, s>>>(xyz, n, partial, aligned16(xyz));
+    TESS_LAUNCH(bounds_partial_kernel, nb, kThreads, 0, s, xyz, n, partial, aligned16(xyz));
     note_launch();
-    bounds_final_kernel<<<1, 32, 0, s>>>(partial, nb, bounds6);
+    TESS_LAUNCH(bounds_final_kernel, 1, 32, 0, s, partial, nb, bounds6);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
     TESS_CUDA_CHECK(cudaFreeAsync(partial, s));
@@ -355,7 +355,7 @@ void launch_bounds(const double* xyz, size_t n, double* bounds6, cudaStream_t s)
 void launch_cell_histogram(const double* xyz, size_t n, const GridSpec& g, uint32_t* cell_of, uint32_t* rank_in_cell, uint32_t* counts, uint32_t* oob_flag, cudaStream_t s) {
     const size_t npairs = (n + 1) / 2;
     if (!npairs) return;
-    cell_histogram_kernel<<<blocks_for(npairs, kThreads), kThreads, 0, s>>>(xyz, n, g, cell_of, rank_in_cell, counts, oob_flag, aligned16(xyz));
+    TESS_LAUNCH(cell_histogram_kernel, blocks_for(npairs, kThreads), kThreads, 0, s, xyz, n, g, cell_of, rank_in_cell, counts, oob_flag, aligned16(xyz));
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -374,7 +374,7 @@ static void launch_scan_impl(const uint32_t* in, OutT* out, size_t n, void* tmp,
     unsigned int* counter = reinterpret_cast<unsigned int*>(tmp);
     unsigned long long* state = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(tmp) + 16);
     const size_t tiles = (n + kScanTile - 1) / kScanTile;
-    scan_kernel<OutT><<<(unsigned int)tiles, kThreads, 0, s>>>(in, out, n, counter, state);
+    TESS_LAUNCH(scan_kernel<OutT>, (unsigned int)tiles, kThreads, 0, s, in, out, n, counter, state);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -386,7 +386,7 @@ void launch_exclusive_scan_u32_to_u64(const uint32_t* in, uint64_t* out, size_t 
 void launch_scatter_records(const double* xyz, const int64_t* ids, const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, Particle* arrived,
                             uint32_t* arrived_idx, size_t n, cudaStream_t s) {
     if (!n) return;
-    scatter_records_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, ids, cell_of, rank_in_cell, delim, arrived, arrived_idx, n);
+    TESS_LAUNCH(scatter_records_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, ids, cell_of, rank_in_cell, delim, arrived, arrived_idx, n);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -394,21 +394,21 @@ void launch_scatter_records(const double* xyz, const int64_t* ids, const uint32_
 void launch_rank_fix(const Particle* arrived, const uint32_t* arrived_idx, const GridSpec& g, const uint32_t* delim, const uint64_t* groups, Particle* sorted,
                      uint32_t* sorted_idx, uint64_t* groups_sorted, size_t n, cudaStream_t s) {
     if (!n) return;
-    rank_fix_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(arrived, arrived_idx, g, delim, groups, sorted, sorted_idx, groups_sorted, n);
+    TESS_LAUNCH(rank_fix_kernel, blocks_for(n, kThreads), kThreads, 0, s, arrived, arrived_idx, g, delim, groups, sorted, sorted_idx, groups_sorted, n);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_plane_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s) {
     if (!n) return;
-    plane_histogram_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, n, g, counts);
+    TESS_LAUNCH(plane_histogram_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, n, g, counts);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, unsigned long long* counts, cudaStream_t s) {
     if (!n) return;
-    pack_count_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, n, g, n_ranks, lo_dev, hi_dev, counts);
+    TESS_LAUNCH(pack_count_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, n, g, n_ranks, lo_dev, hi_dev, counts);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -416,7 +416,7 @@ void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ran
 void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev,
                          const unsigned long long* offsets, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, cudaStream_t s) {
     if (!n) return;
-    pack_scatter_kernel<<<blocks_for(n, kThreads), kThreads, 0, s>>>(xyz, ids, id_base, n, g, n_ranks, lo_dev, hi_dev, offsets, cursors, out_xyz, out_ids);
+    TESS_LAUNCH(pack_scatter_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, ids, id_base, n, g, n_ranks, lo_dev, hi_dev, offsets, cursors, out_xyz, out_ids);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }

@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(128) radius_query_kernel(const QueryParams P) 
 void launch_radius_query(const QueryParams& p, bool fill, cudaStream_t s) {
     if (!p.n_query) return;
     const unsigned int nb = (unsigned int)((p.n_query * 32 + 127) / 128);
-    if (fill) radius_query_kernel<true><<<nb, 128, 0, s>>>(p);
-    else radius_query_kernel<false><<<nb, 128, 0, s>>>(p);
+    if (fill) TESS_LAUNCH(radius_query_kernel<true>, nb, 128, 0, s, p);
+    else TESS_LAUNCH(radius_query_kernel<false>, nb, 128, 0, s, p);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
