@@ -138,21 +138,21 @@ void launch_compact_faces(const uint32_t* status, const uint64_t* offsets, const
                           size_t n_rows, int64_t* nbr, double* area, uint32_t* flen, cudaStream_t s, uint64_t face_cap) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows + kRowsPerBlock - 1) / kRowsPerBlock);
-    compact_faces_kernel<<<nb, 256, 0, s>>>(status, offsets, st_nbr, st_area, st_flen, fstride, n_rows, nbr, area, flen, face_cap);
+    TESS_LAUNCH(compact_faces_kernel, nb, 256, 0, s, status, offsets, st_nbr, st_area, st_flen, fstride, n_rows, nbr, area, flen, face_cap);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_clear_status_bits(uint32_t* status, size_t n, uint32_t bits, cudaStream_t s) {
     if (!n) return;
-    clear_status_bits_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s>>>(status, n, bits);
+    TESS_LAUNCH(clear_status_bits_kernel, (unsigned int)((n + 255) / 256), 256, 0, s, status, n, bits);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_chunk_flags(const uint32_t* row_of_slot, uint32_t slot_begin, size_t n, uint32_t row_lo, uint32_t row_hi, uint32_t* flags, cudaStream_t s) {
     const unsigned int nb = (unsigned int)((n + 1 + 255) / 256);
-    chunk_flags_kernel<<<nb, 256, 0, s>>>(row_of_slot, slot_begin, n, row_lo, row_hi, flags);
+    TESS_LAUNCH(chunk_flags_kernel, nb, 256, 0, s, row_of_slot, slot_begin, n, row_lo, row_hi, flags);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -160,7 +160,7 @@ void launch_chunk_flags(const uint32_t* row_of_slot, uint32_t slot_begin, size_t
 void launch_chunk_scatter(const uint32_t* flags, const uint64_t* pos, uint32_t slot_begin, size_t n, uint32_t* work_slots, cudaStream_t s) {
     if (!n) return;
     const unsigned int nb = (unsigned int)((n + 255) / 256);
-    chunk_scatter_kernel<<<nb, 256, 0, s>>>(flags, pos, slot_begin, n, work_slots);
+    TESS_LAUNCH(chunk_scatter_kernel, nb, 256, 0, s, flags, pos, slot_begin, n, work_slots);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -170,7 +170,7 @@ void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot
                          uint32_t* flen, cudaStream_t s) {
     if (!n_work) return;
     const unsigned int nb = (unsigned int)((n_work * 32 + 127) / 128);
-    compact_redo_kernel<<<nb, 128, 0, s>>>(work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, st_flen, fstride, n_work, nbr, area, flen);
+    TESS_LAUNCH(compact_redo_kernel, nb, 128, 0, s, work_slots, row_of_slot, row_base, nfaces, offsets, st_nbr, st_area, st_flen, fstride, n_work, nbr, area, flen);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -178,7 +178,7 @@ void launch_compact_redo(const uint32_t* work_slots, const uint32_t* row_of_slot
 void launch_gather_vertices(const uint32_t* nverts, const unsigned long long* vbase, const uint64_t* voffsets, const double* pool, size_t n_rows, double* vtx, cudaStream_t s) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
-    gather_vertices_kernel<<<nb, 256, 0, s>>>(nverts, vbase, voffsets, pool, n_rows, vtx);
+    TESS_LAUNCH(gather_vertices_kernel, nb, 256, 0, s, nverts, vbase, voffsets, pool, n_rows, vtx);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -187,7 +187,7 @@ void launch_gather_loops(const uint32_t* nloops, const unsigned long long* lbase
                          uint32_t* out, cudaStream_t s) {
     if (!n_rows) return;
     const unsigned int nb = (unsigned int)((n_rows * 32 + 255) / 256);
-    gather_loops_kernel<<<nb, 256, 0, s>>>(nloops, lbase, face_offsets, fv_offsets, pool, n_rows, out);
+    TESS_LAUNCH(gather_loops_kernel, nb, 256, 0, s, nloops, lbase, face_offsets, fv_offsets, pool, n_rows, out);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }
@@ -196,9 +196,9 @@ void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s)
     constexpr int nb = 296;
     double* partial = nullptr;
     TESS_CUDA_CHECK(cudaMallocAsync(&partial, sizeof(double) * nb, s));
-    volume_partial_kernel<<<nb, 256, 0, s>>>(vol, n, partial);
+    TESS_LAUNCH(volume_partial_kernel, nb, 256, 0, s, vol, n, partial);
     note_launch();
-    volume_final_kernel<<<1, 32, 0, s>>>(partial, nb, out);
+    TESS_LAUNCH(volume_final_kernel, 1, 32, 0, s, partial, nb, out);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
     TESS_CUDA_CHECK(cudaFreeAsync(partial, s));
@@ -207,8 +207,9 @@ void launch_volume_sum(const double* vol, size_t n, double* out, cudaStream_t s)
 }  // namespace tess
 
 // ---------------------------------------------------------------------------------------------
-// telemetry
+// telemetry (not part of the emulated build of tests/emu)
 // ---------------------------------------------------------------------------------------------
+#ifndef TESS_WARP_EMU
 #include <atomic>
 namespace tess {
 namespace {
@@ -255,3 +256,4 @@ double measure_fp64_peak_tflops() {
     return best;
 }
 }  // namespace tess
+#endif  // TESS_WARP_EMU
