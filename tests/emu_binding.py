@@ -219,3 +219,46 @@ def radius_query(grid: EmuGrid, xyz, radius, mode, target_group=-1, os_threads=4
     assert L.emu_query_run(C.byref(a)) == 0
     o = offsets.astype(np.int64)
     return [indices[o[i]:o[i + 1]].tolist() for i in range(m)], flags
+
+
+# ------------------------------------------------------------------------------------------------
+# outputs.cu on the emulator
+# ------------------------------------------------------------------------------------------------
+class PackArgs(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_uint64), ("status", C.c_void_p), ("nfaces", C.c_void_p), ("st_nbr", C.c_void_p), ("st_area", C.c_void_p), ("st_flen", C.c_void_p),
+        ("fstride", C.c_uint32), ("redo_rows", C.c_void_p), ("n_redo", C.c_uint64), ("redo_nbr", C.c_void_p), ("redo_area", C.c_void_p), ("redo_flen", C.c_void_p),
+        ("redo_stride", C.c_uint32), ("offsets", C.c_void_p), ("nbr", C.c_void_p), ("area", C.c_void_p), ("flen", C.c_void_p), ("face_cap", C.c_uint64),
+        ("os_threads", C.c_uint32), ("reverse", C.c_uint32),
+    ]
+
+
+def pack_faces(status, nfaces, st_nbr, st_area, st_flen, fstride, redo_rows=None, redo_nbr=None, redo_area=None, redo_flen=None, redo_stride=0,
+               os_threads=4, reverse=False):
+    """Exclusive scan of the face counts + compact_faces (+ compact_redo): staged rows -> CSR, as tess_compute_all does."""
+    L = _aux_lib("outputs")
+    n = len(status)
+    nf1 = np.concatenate([np.asarray(nfaces, np.uint32), [0]]).astype(np.uint32)
+    total = int(nf1.sum())
+    offsets, nbr, area, flen = np.zeros(n + 1, np.uint64), np.full(total, -99, np.int64), np.full(total, -1.0), np.zeros(total, np.uint32)
+    a = PackArgs()
+    a.n_rows, a.status, a.nfaces = n, status.ctypes.data, nf1.ctypes.data
+    a.st_nbr, a.st_area, a.st_flen, a.fstride = st_nbr.ctypes.data, st_area.ctypes.data, (None if st_flen is None else st_flen.ctypes.data), fstride
+    if redo_rows is not None and len(redo_rows):
+        a.redo_rows, a.n_redo, a.redo_nbr, a.redo_area = redo_rows.ctypes.data, len(redo_rows), redo_nbr.ctypes.data, redo_area.ctypes.data
+        a.redo_flen, a.redo_stride = (None if redo_flen is None else redo_flen.ctypes.data), redo_stride
+    a.offsets, a.nbr, a.area, a.flen, a.face_cap = offsets.ctypes.data, nbr.ctypes.data, area.ctypes.data, (None if st_flen is None else flen.ctypes.data), total
+    a.os_threads, a.reverse = os_threads, int(reverse)
+    assert L.emu_pack_run(C.byref(a)) == 0
+    return offsets.astype(np.int64), nbr, area, flen
+
+
+def outputs_lib():
+    L = _aux_lib("outputs")
+    L.emu_chunk_list.restype = C.c_uint64
+    L.emu_chunk_list.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.emu_volume_sum.restype = C.c_double
+    L.emu_volume_sum.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.emu_gather.argtypes = [C.c_void_p] * 9 + [C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.emu_clear_status_bits.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    return L

@@ -107,3 +107,84 @@ def test_queries_match_oracle_in_order(eb, gen, reverse):
             exp = od.expanding_search(*q).expand_all_in_radius(max_radius)
             assert cloud[i] == exp
             assert only3[i] == [k for k in exp if groups[k] == 3]  # interface.rs:359-362
+
+
+# ------------------------------------------------------------------ outputs.cu ---------------
+ST_LARGE_PATH = 1 << 31
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_csr_packing_of_staged_rows(eb, gen, ob, reverse):
+    """compact_faces + compact_redo (interface.rs:342-384 in batch form): fixed-stride staging rows, some of them
+    recomputed by a larger configuration into their own staging, become the CSR arrays — here the oracle's cells
+    are staged and must come back unchanged."""
+    pts = gen.uniform(3000, 33)
+    r = ob.Diagram(pts, box=list(BOX)).compute_cells(mode=ob.MODE_SECURITY)
+    fo = r.face_offsets
+    n, fstride, rstride = r.n, 40, 128
+    nfaces = np.diff(fo).astype(np.uint32)
+    status = np.zeros(n, np.uint32)
+    redo_rows = np.sort(np.random.default_rng(5).choice(n, 200, replace=False)).astype(np.uint32)
+    status[redo_rows] |= ST_LARGE_PATH
+    st_nbr, st_area, st_flen = np.full(n * fstride, -7, np.int64), np.full(n * fstride, -7.0), np.zeros(n * fstride, np.uint16)
+    for c in range(n):
+        if not status[c] & ST_LARGE_PATH:
+            k = int(nfaces[c])
+            st_nbr[c * fstride: c * fstride + k] = r.cell_neighbors(c)
+            st_area[c * fstride: c * fstride + k] = r.cell_areas(c)
+            st_flen[c * fstride: c * fstride + k] = np.arange(k) + 3
+    rd_nbr, rd_area, rd_flen = np.full(len(redo_rows) * rstride, -8, np.int64), np.full(len(redo_rows) * rstride, -8.0), np.zeros(len(redo_rows) * rstride, np.uint16)
+    for w, c in enumerate(redo_rows):
+        k = int(nfaces[c])
+        rd_nbr[w * rstride: w * rstride + k] = r.cell_neighbors(c)
+        rd_area[w * rstride: w * rstride + k] = r.cell_areas(c)
+        rd_flen[w * rstride: w * rstride + k] = np.arange(k) + 3
+    offsets, nbr, area, flen = eb.pack_faces(status, nfaces, st_nbr, st_area, st_flen, fstride, redo_rows, rd_nbr, rd_area, rd_flen, rstride, reverse=reverse)
+    assert np.array_equal(offsets, fo)
+    assert np.array_equal(nbr, r.neighbors) and np.array_equal(area, r.areas)
+    assert np.array_equal(flen, np.concatenate([np.arange(k) + 3 for k in nfaces]))
+
+
+def test_chunk_work_lists_volume_sum_and_gathers(eb, gen):
+    L = eb.outputs_lib()
+    rng = np.random.default_rng(7)
+    # streaming: rows [lo, hi) as ascending sorted slots
+    n = 5000
+    row_of_slot = rng.permutation(n).astype(np.uint32)
+    work = np.zeros(n, np.uint32)
+    for lo, hi in ((0, 700), (700, 4100), (4100, 5000), (10, 10)):
+        m = L.emu_chunk_list(row_of_slot.ctypes.data, n, lo, hi, work.ctypes.data, 4)
+        exp = np.nonzero((row_of_slot >= lo) & (row_of_slot < hi))[0]
+        assert m == len(exp) and np.array_equal(work[:m], exp)
+    # volume closure sum: deterministic whatever the schedule, equal to the exact sum within rounding
+    vol = rng.random(100_000) / 100_000
+    sums = {L.emu_volume_sum(vol.ctypes.data, len(vol), t, rv) for t in (1, 4) for rv in (0, 1)}
+    assert len(sums) == 1
+    import math
+    assert abs(sums.pop() - math.fsum(vol)) < 1e-13
+    # geometry gathers: per-row blocks of the bump-allocated pools -> CSR order
+    rows = 300
+    nv = rng.integers(4, 30, rows).astype(np.uint32)
+    nf = rng.integers(4, 12, rows).astype(np.uint32)
+    flen = [rng.integers(3, 8, k) for k in nf]
+    nl = np.array([int(f.sum()) for f in flen], np.uint32)
+    order = rng.permutation(rows)  # cells finished in another order than their rows
+    vbase, lbase = np.zeros(rows, np.uint64), np.zeros(rows, np.uint64)
+    cv = cl = 0
+    for c in order:
+        vbase[c], lbase[c] = cv, cl
+        cv += int(nv[c]); cl += int(nl[c])
+    vpool, lpool = rng.random((cv, 3)), rng.integers(0, 30, cl).astype(np.uint32)
+    voff = np.concatenate([[0], np.cumsum(nv)]).astype(np.uint64)
+    face_off = np.concatenate([[0], np.cumsum(nf)]).astype(np.uint64)
+    fv_off = np.concatenate([[0], np.cumsum(np.concatenate(flen))]).astype(np.uint64)
+    vtx, loops = np.zeros((cv, 3)), np.zeros(cl, np.uint32)
+    L.emu_gather(nv.ctypes.data, vbase.ctypes.data, voff.ctypes.data, vpool.ctypes.data, nl.ctypes.data, lbase.ctypes.data, face_off.ctypes.data,
+                 fv_off.ctypes.data, lpool.ctypes.data, rows, vtx.ctypes.data, loops.ctypes.data, 4)
+    for c in range(rows):
+        assert np.array_equal(vtx[int(voff[c]): int(voff[c + 1])], vpool[int(vbase[c]): int(vbase[c]) + int(nv[c])])
+        o = int(fv_off[int(face_off[c])])
+        assert np.array_equal(loops[o: o + int(nl[c])], lpool[int(lbase[c]): int(lbase[c]) + int(nl[c])])
+    st = np.full(1000, 0x80000005, np.uint32)
+    L.emu_clear_status_bits(st.ctypes.data, 1000, 0x80000000)
+    assert np.all(st == 5)
