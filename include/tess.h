@@ -219,7 +219,7 @@ int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t i
 /* ---- Telemetry used by bench.py ----------------------------------------------------------- */
 
 /* CUDA-event durations (ms, on the launching stream) of the last computation:
- * ms[0] clip kernel (small-cell pass), ms[1] large-cell redo pass, ms[2] scans + CSR compaction, ms[3] whole call. */
+ * ms[0] clip kernel (small-cell pass), ms[1] redo passes (wider table, medium and large configurations), ms[2] scans + CSR compaction, ms[3] whole call. */
 int tess_result_timings(const tess_result* r, double ms[4]);
 /* ms[0] = binning pass (histogram + scan + scatter + gather) of the last initialize. */
 int tess_diagram_timings(const tess_diagram* d, double ms[1]);

@@ -131,7 +131,7 @@ class CellBatch:
         return float(out.value)
 
     def timings(self) -> dict:
-        """CUDA-event durations in ms: clip kernel, large-cell redo, scans + compaction, whole call."""
+        """CUDA-event durations in ms: clip kernel, redo passes (medium / large configurations), scans + compaction, whole call."""
         arr = (C.c_double * 4)()
         check(_lib.lib().tess_result_timings(self._h, C.byref(arr)))
         return dict(clip_ms=arr[0], redo_ms=arr[1], outputs_ms=arr[2], total_ms=arr[3])
