@@ -1074,6 +1074,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
 #define rej_ok(r2_) (radius_mode || (r2_) < stop_thr)
         bool done = false;
         bool failed = false;
+        bool stale_thr = false;  // the threshold lags behind the last cuts (non-counting instantiation only)
 
         for (uint32_t t0 = 0; !done; t0 += 32) {
             // ---- 32 search_order entries, one per lane (celery.rs:981-1014) -------------------
@@ -1184,6 +1185,12 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     const int l = __ffs(pending) - 1;
                     pending &= pending - 1;
                     if ((marker_lanes >> l) & 1u) {
+                        if (stale_thr) {  // a plane this rank does not hold: decide with the exact threshold
+                            stop_thr = mul(4.0, M.max_radius_sq());
+                            stale_thr = false;
+                            pending &= __ballot_sync(FULL, cand && !(src_key > stop_thr) && (src_marker || rej_ok(r2)));
+                            if (__shfl_sync(FULL, (int)(src_key > stop_thr), l)) continue;
+                        }
                         status |= ST_HALO_INSUFFICIENT;
                         continue;
                     }
@@ -1211,6 +1218,14 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     if (rc == 1) {
                         c_cuts += 1;
                         if (!radius_mode) {
+                            if (!COUNT) {
+                                // The threshold only ever rejects planes that cannot cut (header comment): without
+                                // work counters it may lag behind.  It is brought up to date once per tile, not after
+                                // every cut; the few planes it would have dropped meanwhile are classified (no vertex
+                                // is Outside) or screened out.
+                                stale_thr = true;
+                                continue;
+                            }
                             // candidates up to this lane were offered under the old threshold
                             const uint32_t upto = uncounted & ((2u << l) - 1u);
                             c_vis += __popc(upto & __ballot_sync(FULL, !(src_key > stop_thr)));
@@ -1219,6 +1234,10 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                             pending &= __ballot_sync(FULL, cand && !(src_key > stop_thr) && (src_marker || rej_ok(r2)));
                         }
                     }
+                }
+                if (stale_thr && !failed) {
+                    stop_thr = mul(4.0, M.max_radius_sq());
+                    stale_thr = false;
                 }
                 c_vis += __popc(uncounted & __ballot_sync(FULL, !(src_key > stop_thr)));
                 // the walk stops at the first entry whose key exceeds the threshold (celery.rs:1036)
