@@ -426,7 +426,8 @@ def main():
         roofline_issue = {"kernel": "clip_kernel<SmallCfg>", "bound": "issue", "achieved": ach, "peak": peak, "unit": "T warp-instr/s", "frac": ach / peak,
                           "warp_instructions_per_cell": inst_per_cell,
                           "peak_source": "%d SMs x 4 schedulers x %.0f MHz (median SM clock under load)" % (sms, clocks["sm_mhz"]),
-                          "note": "instruction count from profiles/clip_kernel_traffic.json (ncu, uniform 10M capture); ncu's own smsp__issue_active for that capture is %.1f %%" % traffic.get("issue_active_pct", float("nan"))}
+                          "note": "instruction count from profiles/clip_kernel_traffic.json (ncu, uniform 10M capture); ncu's own smsp__issue_active for that capture is %.1f %%" % traffic.get("issue_active_pct", float("nan")),
+                          "capture_note": traffic.get("capture_is_one_change_behind")}
     bin_avg = float(np.mean(bin_ms))
     n_binned = (state["res"].n_received if world > 1 else n_local)
     bin_ach = BYTES_PER_POINT_BINNING * n_binned / (bin_avg * 1e-3) / 1e9
