@@ -70,6 +70,8 @@ struct emu_clip_args {
     // emulator
     uint32_t os_threads, blocks, reverse;
     uint64_t collectives;   // out
+    // slab diagrams: the x-planes [local_lo, local_hi) are held (delim covers only them); 0, 0 = all
+    uint32_t local_lo, local_hi;
 };
 
 int emu_clip_run(emu_clip_args* a) {
@@ -98,6 +100,7 @@ int emu_clip_run(emu_clip_args* a) {
     g.ix = a->cell_info[3]; g.iy = a->cell_info[4]; g.iz = a->cell_info[5];
     g.cpd = a->cpd;
     g.local_lo = 0; g.local_hi = a->cpd; g.own_lo = 0; g.own_hi = a->cpd;
+    if (a->local_hi > a->local_lo) { g.local_lo = g.own_lo = a->local_lo; g.local_hi = g.own_hi = a->local_hi; }
     for (int i = 0; i < 6; ++i) P.box[i] = a->box[i];
     P.slot_begin = 0;
     P.n_work = a->n_work;

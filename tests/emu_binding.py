@@ -27,6 +27,7 @@ class Args(C.Structure):
         ("gv_xyz", C.c_void_p), ("gl_idx", C.c_void_p), ("gv_cap", C.c_uint64), ("gl_cap", C.c_uint64), ("g_cursor", C.c_void_p),
         ("nverts", C.c_void_p), ("nloops", C.c_void_p), ("vbase", C.c_void_p), ("lbase", C.c_void_p), ("st_flen", C.c_void_p),
         ("os_threads", C.c_uint32), ("blocks", C.c_uint32), ("reverse", C.c_uint32), ("collectives", C.c_uint64),
+        ("local_lo", C.c_uint32), ("local_hi", C.c_uint32),
     ]
 
 
@@ -92,6 +93,21 @@ class EmuGrid:
         self.box = np.asarray(box, np.float64)
         self.groups_sorted = None if groups is None else np.ascontiguousarray(np.asarray(groups, np.uint64)[self.sorted_indices])
         assert self.delim.size == self.cpd ** 3 + 1
+        self.local = (0, 0)
+
+    def restrict_to_planes(self, points, local):
+        """Turn this grid into the slab diagram of a rank that holds only the x-planes [local[0], local[1]): the
+        particles of those planes are binned — by the emulated grid.cu, with their global ids — into a slab-local
+        delimiter array, as tess_diagram_initialize_slab does.  Returns the global ids in slab slot order."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        cpd = self.cpd
+        gx = (self.oracle.cells() // (cpd * cpd)).astype(np.int64)
+        sel = np.nonzero((gx >= local[0]) & (gx < local[1]))[0]
+        b = binning(pts[sel], self.oracle, ids=sel.astype(np.int64), local=local)
+        assert b["oob"] == 0
+        self.particles, self.delim, self.n, self.local = np.ascontiguousarray(b["sorted"]), b["delim"], len(sel), tuple(local)
+        self.sorted_indices = b["sorted"][:, 3].view(np.int64).copy()
+        return self.sorted_indices
 
     def clip(self, work_slots=None, large=False, flags=0, search_radius=float("nan"), target_group=-1, os_threads=8, reverse=False, fstride=None,
              query_xyz=None, want_vertices=False, count=True):
@@ -129,6 +145,7 @@ class EmuGrid:
         a.st_nbr, a.st_area, a.counters = st_nbr.ctypes.data, st_area.ctypes.data, (counters.ctypes.data if count else None)
         a.failed_slots, a.n_failed = failed.ctypes.data, n_failed.ctypes.data
         a.os_threads, a.blocks, a.reverse = os_threads, os_threads, int(reverse)
+        a.local_lo, a.local_hi = self.local
         rc = L.emu_clip_run(C.byref(a))
         assert rc == 0
         e = EmuCells(vol, nfaces, status, cell_id, st_nbr, st_area, fstride, counters, n_failed, failed, a.collectives)

@@ -194,3 +194,34 @@ def test_other_scales_and_oblong_boxes(eb, gen, scale):
     for k in ("visited", "tested", "vertex_classifications", "cuts", "new_vertices", "faces"):
         assert e.counters[k] == r.counters[k], k
     assert abs(e.volumes.sum() / (0.75 * scale ** 3) - 1.0) < 1e-12
+
+
+def test_slab_with_a_thin_halo_flags_the_same_cells_in_both_instantiations(eb, gen):
+    """A rank that holds too few ghost planes: a search that reaches a plane it does not hold flags the cell
+    (TESS_STATUS_HALO_INSUFFICIENT) instead of being silently wrong.  The instantiation without work counters lets
+    its termination threshold lag behind the cuts; the flags must still be exactly those of the counting one."""
+    pts = gen.uniform(6000, 77)
+    g = eb.EmuGrid(pts, BOX)
+    whole = g.oracle_cells(slots=None)  # rows in global grid order
+    gid_of_row = g.sorted_indices.copy()
+    lo, hi = g.cpd // 3, g.cpd // 3 + 5
+    ids = g.restrict_to_planes(pts, (lo, hi))
+    cpd = g.cpd
+    gx = g.oracle.cells().astype(np.int64)[ids] // (cpd * cpd)
+    own = np.nonzero((gx >= lo + 1) & (gx < hi - 1))[0].astype(np.uint32)  # one ghost plane per side: too thin
+    a = g.clip(work_slots=own, count=True)
+    b = g.clip(work_slots=own, count=False)
+    flagged = (a.status & 0x8) != 0
+    assert flagged.any() and not flagged.all()
+    assert np.array_equal(a.status, b.status)
+    assert np.array_equal(a.volumes, b.volumes) and np.array_equal(a.neighbors, b.neighbors) and np.array_equal(a.areas, b.areas)
+    # unflagged cells are the cells of the whole diagram
+    row_of_gid = np.empty(len(pts), np.int64)
+    row_of_gid[gid_of_row] = np.arange(len(pts))
+    rows = row_of_gid[ids[own]]
+    okc = ~flagged & ((a.status & BAD) == 0)
+    assert okc.sum() > 100
+    assert np.array_equal(a.volumes[okc], whole.volumes[rows[okc]])
+    fo = whole.face_offsets
+    for k in np.nonzero(okc)[0][::37]:
+        assert a.neighbors[a.face_offsets[k]: a.face_offsets[k + 1]].tolist() == whole.neighbors[fo[rows[k]]: fo[rows[k] + 1]].tolist()
