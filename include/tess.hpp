@@ -229,6 +229,28 @@ class Cell {
     std::vector<VoronoiFace> compute_faces();                 // interface.rs:373-384
     std::optional<size_t> original_index() const { return index_; }  // interface.rs:387-389
     uint32_t status() { return need().status[row_]; }
+    /// interface.rs:348-365: ExpandingSearch::expand_all_in_radius(radius) around the cell's position (particle ids in
+    /// search-table order), filtered by group.  A cell made by index needs its position: pass the particle's coordinates
+    /// (the mirror does not keep a host copy of the points).
+    std::vector<size_t> compute_neighbor_cloud(const Vector3& position, double radius, std::optional<size_t> target_group = std::nullopt) const {
+        tess_query* q = nullptr;
+        check(tess_find_neighbors(diagram_->handle(), reinterpret_cast<const double*>(&position), 1, radius, TESS_QUERY_NEIGHBOR_CLOUD,
+                                  target_group ? static_cast<int64_t>(*target_group) : int64_t(-1), nullptr, &q));
+        const uint64_t* off = nullptr;
+        const int64_t* idx = nullptr;
+        std::vector<size_t> out;
+        const int rc1 = tess_query_offsets(q, &off), rc2 = tess_query_indices(q, &idx);
+        if (rc1 == TESS_OK && rc2 == TESS_OK) out.assign(idx + off[0], idx + off[1]);
+        tess_query_free(q);
+        check(rc1);
+        check(rc2);
+        return out;
+    }
+    /// ... for a cell made by get_cell_at_particle the position is the cell's own
+    std::vector<size_t> compute_neighbor_cloud(double radius, std::optional<size_t> target_group = std::nullopt) const {
+        if (index_) throw Error(TESS_ERR_STATE, "compute_neighbor_cloud(radius): a cell made by index must be given its particle's position");
+        return compute_neighbor_cloud(position_, radius, target_group);
+    }
 
    private:
     friend class Diagram;

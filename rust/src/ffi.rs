@@ -10,6 +10,10 @@ pub struct tess_diagram {
 pub struct tess_result {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct tess_query {
+    _private: [u8; 0],
+}
 
 pub const TESS_OK: c_int = 0;
 pub const TESS_F64: c_int = 0;
@@ -17,6 +21,9 @@ pub const TESS_OUT_VOLUME: u32 = 1;
 pub const TESS_OUT_NEIGHBORS: u32 = 2;
 pub const TESS_OUT_AREAS: u32 = 4;
 pub const TESS_OUT_VERTICES: u32 = 8;
+pub const TESS_QUERY_CELL_RADIUS: c_int = 0;
+pub const TESS_QUERY_REAL_RADIUS: c_int = 1;
+pub const TESS_QUERY_NEIGHBOR_CLOUD: c_int = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -49,4 +56,20 @@ extern "C" {
     pub fn tess_result_status(r: *mut tess_result, out: *mut *const u32) -> c_int;
     pub fn tess_result_vertex_offsets(r: *mut tess_result, out: *mut *const u64) -> c_int;
     pub fn tess_result_vertices(r: *mut tess_result, out: *mut *const f64) -> c_int;
+    pub fn tess_result_face_vertex_offsets(r: *mut tess_result, out: *mut *const u64) -> c_int;
+    pub fn tess_result_face_vertex_indices(r: *mut tess_result, out: *mut *const u32) -> c_int;
+    pub fn tess_result_cell_ids(r: *mut tess_result, out: *mut *const i64) -> c_int;
+    pub fn tess_result_counters(r: *mut tess_result, counters: *mut u64) -> c_int;
+    pub fn tess_result_volume_sum(r: *mut tess_result, out: *mut f64) -> c_int;
+    pub fn tess_version() -> c_int;
+    pub fn tess_device_count() -> c_int;
+    pub fn tess_diagram_clear(d: *mut tess_diagram) -> c_int;
+    pub fn tess_kernel_launch_count() -> u64;
+    // radius / neighbour-cloud queries (celery.rs:802-855, :1023-1075; interface.rs:348-365)
+    pub fn tess_find_neighbors(d: *const tess_diagram, xyz: *const f64, m: usize, radius: f64, mode: c_int, target_group: i64, stream: *mut c_void,
+                               out: *mut *mut tess_query) -> c_int;
+    pub fn tess_query_free(q: *mut tess_query);
+    pub fn tess_query_offsets(q: *mut tess_query, out: *mut *const u64) -> c_int;
+    pub fn tess_query_indices(q: *mut tess_query, out: *mut *const i64) -> c_int;
+    pub fn tess_query_status(q: *mut tess_query, out: *mut *const u32) -> c_int;
 }

@@ -59,6 +59,11 @@ struct Batch {
     face_offsets: *const u64,
     neighbors: *const i64,
     areas: *const f64,
+    // TESS_OUT_VERTICES: per-cell vertex lists and per-face loops (indices into the owning cell's list)
+    vertex_offsets: *const u64,
+    vertices: *const f64,
+    face_vertex_offsets: *const u64,
+    face_vertex_indices: *const u32,
 }
 impl Drop for Batch {
     fn drop(&mut self) {
@@ -135,15 +140,31 @@ impl<PointType: ToCeleryPoint<f64>> Diagram<PointType> {
         if let Some(g) = target_group {
             o.target_group = g as i64;
         }
+        // Cell::compute_vertices / VoronoiFace::compute_vertices read the geometry outputs
+        o.outputs |= ffi::TESS_OUT_VERTICES;
         o
     }
     fn wrap(r: *mut ffi::tess_result) -> Rc<Batch> {
-        let mut b = Batch { r, volumes: ptr::null(), face_offsets: ptr::null(), neighbors: ptr::null(), areas: ptr::null() };
+        let mut b = Batch {
+            r,
+            volumes: ptr::null(),
+            face_offsets: ptr::null(),
+            neighbors: ptr::null(),
+            areas: ptr::null(),
+            vertex_offsets: ptr::null(),
+            vertices: ptr::null(),
+            face_vertex_offsets: ptr::null(),
+            face_vertex_indices: ptr::null(),
+        };
         unsafe {
             check(ffi::tess_result_volumes(r, &mut b.volumes));
             check(ffi::tess_result_face_offsets(r, &mut b.face_offsets));
             check(ffi::tess_result_neighbors(r, &mut b.neighbors));
             check(ffi::tess_result_areas(r, &mut b.areas));
+            check(ffi::tess_result_vertex_offsets(r, &mut b.vertex_offsets));
+            check(ffi::tess_result_vertices(r, &mut b.vertices));
+            check(ffi::tess_result_face_vertex_offsets(r, &mut b.face_vertex_offsets));
+            check(ffi::tess_result_face_vertex_indices(r, &mut b.face_vertex_indices));
         }
         Rc::new(b)
     }
@@ -158,6 +179,15 @@ impl<PointType: ToCeleryPoint<f64>> Diagram<PointType> {
         let b = Self::wrap(r);
         self.batches.borrow_mut().push((key, target_group, b.clone()));
         b
+    }
+
+    /// Extension: every cell of the diagram in one batch (what the first `compute_voronoi_cell` triggers anyway).
+    pub fn compute_all_cells(&self, search_radius: Option<f64>, target_group: Option<usize>) {
+        let _ = self.batch(search_radius, target_group);
+    }
+    /// Number of particles added so far.
+    pub fn len(&self) -> usize {
+        self.points.len()
     }
 
     /// interface.rs:186-208
@@ -226,11 +256,43 @@ impl<'a, PointType: ToCeleryPoint<f64>> Cell<'a, PointType> {
         let (lo, hi) = Self::range(&b, self.row);
         (lo..hi).map(|k| wall_neighbor(unsafe { *b.neighbors.add(k) })).collect()
     }
+    /// interface.rs:348-365: `ExpandingSearch::expand_all_in_radius(radius)` around the cell's position (particle
+    /// indices in search-table order), then only the members of `target_group` if one is given.
+    pub fn compute_neighbor_cloud(&self, radius: f64, target_group: Option<usize>) -> Vec<usize> {
+        let mut q = ptr::null_mut();
+        let group = match target_group {
+            Some(g) => g as i64,
+            None => -1,
+        };
+        check(unsafe {
+            ffi::tess_find_neighbors(self.diagram.d, &self.position as *const Vector3 as *const f64, 1, radius, ffi::TESS_QUERY_NEIGHBOR_CLOUD, group, ptr::null_mut(), &mut q)
+        });
+        let mut offsets: *const u64 = ptr::null();
+        let mut indices: *const i64 = ptr::null();
+        let (rc1, rc2) = unsafe { (ffi::tess_query_offsets(q, &mut offsets), ffi::tess_query_indices(q, &mut indices)) };
+        let mut out = Vec::new();
+        if rc1 == ffi::TESS_OK && rc2 == ffi::TESS_OK {
+            let (lo, hi) = unsafe { (*offsets as usize, *offsets.add(1) as usize) };
+            out.extend((lo..hi).map(|k| (unsafe { *indices.add(k) }) as usize));
+        }
+        unsafe { ffi::tess_query_free(q) };
+        check(rc1);
+        check(rc2);
+        out
+    }
+    /// interface.rs:368-370: the vertices of the cell, in cell-local coordinates (relative to the particle, as the
+    /// reference's polyhedron is translated by -position, interface.rs:266).
+    pub fn compute_vertices(&mut self) -> Vec<Vector3> {
+        let b = self.need();
+        let (lo, hi) = unsafe { (*b.vertex_offsets.add(self.row) as usize, *b.vertex_offsets.add(self.row + 1) as usize) };
+        (lo..hi).map(|v| unsafe { Vector3 { x: *b.vertices.add(3 * v), y: *b.vertices.add(3 * v + 1), z: *b.vertices.add(3 * v + 2) } }).collect()
+    }
     /// interface.rs:373-384
     pub fn compute_faces(&mut self) -> Vec<VoronoiFace> {
         let b = self.need();
         let (lo, hi) = Self::range(&b, self.row);
-        (lo..hi).map(|k| VoronoiFace { batch: b.clone(), k }).collect()
+        let row = self.row;
+        (lo..hi).map(|k| VoronoiFace { batch: b.clone(), k, row }).collect()
     }
     /// interface.rs:387-389
     pub fn original_index(&self) -> Option<usize> {
@@ -242,8 +304,22 @@ impl<'a, PointType: ToCeleryPoint<f64>> Cell<'a, PointType> {
 pub struct VoronoiFace {
     batch: Rc<Batch>,
     k: usize,
+    row: usize,
 }
 impl VoronoiFace {
+    /// interface.rs:403-405 -> Polyhedron::compute_face_vertices (polyhedron.rs:897-919): the face's vertices in loop
+    /// order, starting at the target of the face's starting edge.
+    pub fn compute_vertices(&self) -> Vec<Vector3> {
+        let b = &self.batch;
+        let base = unsafe { *b.vertex_offsets.add(self.row) as usize };
+        let (lo, hi) = unsafe { (*b.face_vertex_offsets.add(self.k) as usize, *b.face_vertex_offsets.add(self.k + 1) as usize) };
+        (lo..hi)
+            .map(|i| unsafe {
+                let v = base + *b.face_vertex_indices.add(i) as usize;
+                Vector3 { x: *b.vertices.add(3 * v), y: *b.vertices.add(3 * v + 1), z: *b.vertices.add(3 * v + 2) }
+            })
+            .collect()
+    }
     /// interface.rs:408-410
     pub fn compute_area(&self) -> f64 {
         unsafe { *self.batch.areas.add(self.k) }
