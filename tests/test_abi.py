@@ -69,3 +69,28 @@ def test_generators_are_pure_integer_streams(gen):
     b = gen.bcc(4, 5)
     assert b.shape == (128, 3) and np.all((b > 0) & (b < 1))
     assert np.array_equal(gen.bcc(4, 5, start=10, count=7), b[10:17])
+
+
+def test_rust_ffi_declares_only_functions_of_the_header():
+    """rust/ cannot be compiled here (no rustc): at least every `fn tess_*` of ffi.rs must exist in include/tess.h with the
+    same number of parameters, and every ffi function used by interface.rs must be declared."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "tess.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    c_decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(tess_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)}
+    ffi = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
+    r_decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (tess_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->[^;]+)?;", ffi, flags=re.S)}
+    assert len(r_decl) >= 30
+
+    def arity(args: str) -> int:
+        args = args.strip()
+        return 0 if args in ("", "void") else args.count(",") + 1
+
+    for name, args in r_decl.items():
+        assert name in c_decl, f"{name} is not in tess.h"
+        assert arity(args) == arity(c_decl[name]), f"{name}: {arity(args)} parameters in ffi.rs, {arity(c_decl[name])} in tess.h"
+    used = set(re.findall(r"ffi::(tess_[a-z0-9_]+)", open(os.path.join(root, "rust", "src", "interface.rs")).read()))
+    types = set(re.findall(r"pub struct (tess_[a-z0-9_]+)", ffi))
+    assert used - types <= set(r_decl), used - types - set(r_decl)
