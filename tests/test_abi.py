@@ -58,6 +58,24 @@ def test_product_never_touches_the_oracle():
                 assert "liboracle" not in txt and "oracle_binding" not in txt and "tess_oracle" not in txt, os.path.join(base, f)
 
 
+def test_product_has_no_cpu_path():
+    """The CPU warp emulator (tests/emu) is test infrastructure too.  The kernel sources carry its hooks behind
+    TESS_WARP_EMU, which only tests/emu/shim defines: the package's Python never mentions it, the package's Makefile
+    never defines it, and the built library holds no emulator symbol."""
+    import subprocess
+
+    pkg = os.path.join(ROOT, "the-tessellator_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(base, f)
+            if f.endswith(".py") or f == "Makefile":
+                txt = open(path, errors="replace").read()
+                assert "TESS_WARP_EMU" not in txt and "warp_emu" not in txt and "libemu" not in txt and "tests/emu" not in txt, path
+    lib = os.path.join(pkg, "libtess_b200.so")
+    syms = subprocess.run(["nm", "-D", "-C", lib], capture_output=True, text=True).stdout + subprocess.run(["nm", "-C", lib], capture_output=True, text=True).stdout
+    assert "emu::" not in syms and "emu_launch" not in syms
+
+
 def test_generators_are_pure_integer_streams(gen):
     import numpy as np
 
