@@ -225,3 +225,26 @@ def test_slab_with_a_thin_halo_flags_the_same_cells_in_both_instantiations(eb, g
     fo = whole.face_offsets
     for k in np.nonzero(okc)[0][::37]:
         assert a.neighbors[a.face_offsets[k]: a.face_offsets[k + 1]].tolist() == whole.neighbors[fo[rows[k]]: fo[rows[k] + 1]].tolist()
+
+
+def test_small_configuration_without_the_serial_walk(eb, gen):
+    """CLIP_SMALL_FAST: the instantiation that has no serial walk finishes every cell whose planes never touch a
+    vertex, bit for bit, and hands the others back flagged like cells that ran out of table; CLIP_SMALL finishes those."""
+    pts = np.concatenate([gen.uniform(2500, 5), 0.25 + 0.5 * gen.simple_cubic(6)])  # random cells around an exact lattice
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    r = g.oracle_cells()
+    for count in (False, True):
+        e = g.clip(large="fast", count=count)
+        handed_back = (e.status & 0x2) != 0
+        assert handed_back.any() and (~handed_back).sum() > 1500
+        assert not (e.status & (0x4 | 0x10)).any()
+        ok = _check(e, r, "fast", expect_all=False)
+        assert np.array_equal(ok, ~handed_back)
+        slots = np.nonzero(handed_back)[0].astype(np.uint32)
+        e2 = g.clip(work_slots=slots, count=count)
+        _check(e2, g.oracle_cells(slots=slots), "redone with the serial walk")
+    # purely random input never needs the walk
+    g2 = eb.EmuGrid(gen.uniform(4000, 6), BOX)
+    e = g2.clip(large="fast", count=False)
+    assert not (e.status & 0x2).any() or g2.table_full == 0
+    _check(e, g2.oracle_cells(), "fast on random input", expect_all=False)

@@ -682,6 +682,10 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
     P.flags = (std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u) | (std::getenv("TESS_FORCE_SWEEP") ? 2u : 0u);
+    // A/B switch (off by default, not yet timed on a GPU): run the main pass with the instantiation that has no serial
+    // walk and no divergence guards (clip.cu, CLIP_SMALL_FAST); cells that need the walk come back flagged like cells
+    // that ran out of table and take redo pass A, which has it.  Query cells are never redone, so they keep CLIP_SMALL.
+    const int main_tier = (std::getenv("TESS_FAST_MAIN_PASS") && !query) ? CLIP_SMALL_FAST : CLIP_SMALL;
     // ---- the pipeline ------------------------------------------------------------------------------
     // The rows are computed in C chunks (C = 1 unless the results stream to host buffers,
     // tess_compute_all_to_host).  Per chunk: clip its cells in sorted (spatial) order; redo what the
@@ -760,7 +764,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
             Q.n_work = (uint32_t)(r1 - r0);
         }
         TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c], s));
-        launch_clip(Q, CLIP_SMALL, s);
+        launch_clip(Q, main_tier, s);
         TESS_CUDA_CHECK(cudaEventRecord(E.ev[3 * c + 1], s));
         // failures so far: [0] all, [1] those that only ran out of search table
         TESS_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(E.pinned + 4 * c), ctrl + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -247,9 +247,15 @@ struct Mesh {
         return -1;
     }
     // Pool::add for faces (pool.rs:85-110): most recently freed slot first, else append
-    __device__ __forceinline__ int alloc_face() {
+    // uniform_slot: pass the slot read from shared memory through a warp reduction.  Every lane reads the same value
+    // anyway; the reduction makes that visible to the compiler, which otherwise treats the face mask — and every
+    // branch that depends on it — as lane-dependent and guards each later collective with a divergence check.
+    __device__ __forceinline__ int alloc_face(bool uniform_slot = false) {
         int slot;
-        if (f_top > 0) slot = (int)sm->fstack[--f_top];
+        if (f_top > 0) {
+            slot = (int)sm->fstack[--f_top];
+            if (uniform_slot) slot = (int)__reduce_max_sync(FULL, (uint32_t)slot);
+        }
         else if (f_hwm < Cfg::FMAX) slot = f_hwm++;
         else return -1;
         flive.set((uint32_t)slot);
@@ -350,6 +356,7 @@ struct Mesh {
 };
 
 constexpr int CUT_FALLBACK = 3;
+constexpr int CUT_NEEDS_SERIAL = -3;
 
 // ---------------------------------------------------------------------------------------------
 // Warp-parallel form of Polyhedron::cut_with_plane (polyhedron.rs:438-642) for the generic case:
@@ -370,7 +377,7 @@ constexpr int CUT_FALLBACK = 3;
 // areas and volumes — are identical to the serial walk's.
 // Returns 1 (cut), CUT_FALLBACK (let the serial walk decide) or -1 (table overflow).
 // ---------------------------------------------------------------------------------------------
-template <class Cfg>
+template <class Cfg, bool SERIAL>
 __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& cnt_nv, bool sweep_only) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
@@ -539,7 +546,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         const int efree_n = M.e_top + (Cfg::E_LIMIT - M.e_hwm);
         if ((int)K > vfree_n || 2 * (int)K + 1 > efree_n) return -1;
     }
-    const int cap_face = M.alloc_face();
+    const int cap_face = M.alloc_face(/*uniform_slot=*/!SERIAL);
     if (cap_face < 0) return -1;
     // first free vertex slots, in ascending order (what repeated lowest-free-bit allocation yields)
     {
@@ -724,7 +731,11 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
 // One plane against the mesh: Polyhedron::cut_with_plane (polyhedron.rs:438-642).
 // Returns 0 = no cut, 1 = cut, 2 = skipped (D17), <0 = capacity overflow / inconsistency.
 // ---------------------------------------------------------------------------------------------
-template <class Cfg>
+// SERIAL = false compiles the reference-shaped serial walk out: a plane that needs it (a vertex on the plane, a cut
+// the lane-parallel form declines) returns CUT_NEEDS_SERIAL and the cell is redone by an instantiation that has it.
+// Without the walk — whose loops run on values read from shared memory — and with alloc_face's uniform slot the
+// compiler can prove the warp converged at every collective of the kernel and drops its divergence guards.
+template <class Cfg, bool SERIAL>
 __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id, uint32_t& status, uint32_t& cnt_vc, uint32_t& cnt_nv, bool serial_only,
                               bool sweep_only) {
     using MeshT = Mesh<Cfg>;
@@ -770,9 +781,10 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     // ---- fast path: no vertex on the plane -> the whole cut in lane-parallel form ----------------
     if (!any_incident && !serial_only) {
         __syncwarp();
-        const int rc = cut_parallel<Cfg>(M, pl, neighbor_id, cnt_nv, sweep_only);
+        const int rc = cut_parallel<Cfg, SERIAL>(M, pl, neighbor_id, cnt_nv, sweep_only);
         if (rc != CUT_FALLBACK) return rc;
     }
+    if constexpr (!SERIAL) return CUT_NEEDS_SERIAL;
 
     // ---- first edge (slot order) with target Inside whose flip's target is Outside; the walk
     //      starts on the flip (polyhedron.rs:413-432) ---------------------------------------------
@@ -1014,7 +1026,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
 // The kernel: persistent warps pull cells from a work counter.
 // ---------------------------------------------------------------------------------------------
 // COUNT: also accumulate the work counters (a separate instantiation keeps them out of the timed kernel).
-template <class Cfg, bool COUNT>
+template <class Cfg, bool COUNT, bool SERIAL = true>
 __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const ClipParams P) {
     using MeshT = Mesh<Cfg>;
     using EW = typename Cfg::EdgeWord;
@@ -1207,9 +1219,11 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     const Plane pl = {pq.x, pq.y, pq.z, pq.w};
                     const long long nid = sm->cand_id[l];
                     c_test += 1;
-                    const int rc = cut_with_plane<Cfg>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u, (P.flags & 2u) != 0u);
+                    const int rc = cut_with_plane<Cfg, SERIAL>(M, pl, nid, status, c_vc, c_nv, (P.flags & 1u) != 0u, (P.flags & 2u) != 0u);
                     if (rc < 0) {
                         if (rc == -1) status |= ST_CAPACITY_OVERFLOW;
+                        // queued like a cell that ran out of table: redone by the small configuration WITH the serial walk
+                        if (rc == CUT_NEEDS_SERIAL) status |= ST_TABLE_EXHAUSTED;
                         failed = true;
                         done = true;
                         break;
@@ -1452,22 +1466,22 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
     }
 }
 
-template <class Cfg, bool COUNT>
+template <class Cfg, bool COUNT, bool SERIAL = true>
 void launch_cfg(const ClipParams& p, cudaStream_t s) {
     if (!p.n_work) return;
     const size_t smem = sizeof(WarpSmem<Cfg>) * Cfg::WARPS;
 #ifdef TESS_WARP_EMU
     *p.work_counter = 0u;
-    emu_launch_kernel([](const void* a) { clip_kernel<Cfg, COUNT>(*static_cast<const ClipParams*>(a)); }, &p, Cfg::WARPS * 32, smem);
+    emu_launch_kernel([](const void* a) { clip_kernel<Cfg, COUNT, SERIAL>(*static_cast<const ClipParams*>(a)); }, &p, Cfg::WARPS * 32, smem);
 #else
     static bool configured = false;
     static int per_sm_cached = 0, sms_cached = 0;
     if (!configured) {
-        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg, COUNT, SERIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
         TESS_CUDA_CHECK(cudaGetDevice(&dev));
         TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev));
-        TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, clip_kernel<Cfg, COUNT>, Cfg::WARPS * 32, smem));
+        TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, clip_kernel<Cfg, COUNT, SERIAL>, Cfg::WARPS * 32, smem));
         configured = true;
     }
     int sms = sms_cached, per_sm = per_sm_cached;
@@ -1476,7 +1490,7 @@ void launch_cfg(const ClipParams& p, cudaStream_t s) {
     const unsigned int want = (unsigned int)((p.n_work + Cfg::WARPS - 1) / Cfg::WARPS);
     const unsigned int grid = std::min<unsigned int>(want, (unsigned int)(sms * per_sm));
     TESS_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s));
-    clip_kernel<Cfg, COUNT><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
+    clip_kernel<Cfg, COUNT, SERIAL><<<grid, Cfg::WARPS * 32, smem, s>>>(p);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -1490,6 +1504,8 @@ void launch_clip(const ClipParams& p, int tier, cudaStream_t s) {
         if (count) launch_cfg<LargeCfg, true>(p, s); else launch_cfg<LargeCfg, false>(p, s);
     } else if (tier == CLIP_MEDIUM) {
         if (count) launch_cfg<MediumCfg, true>(p, s); else launch_cfg<MediumCfg, false>(p, s);
+    } else if (tier == CLIP_SMALL_FAST) {
+        if (count) launch_cfg<SmallCfg, true, false>(p, s); else launch_cfg<SmallCfg, false, false>(p, s);
     } else {
         if (count) launch_cfg<SmallCfg, true>(p, s); else launch_cfg<SmallCfg, false>(p, s);
     }

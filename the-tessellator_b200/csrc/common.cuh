@@ -143,7 +143,9 @@ void launch_plane_histogram(const double* xyz, size_t n, const GridSpec& g, unsi
 void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, unsigned long long* counts, cudaStream_t s);
 void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, const unsigned long long* offsets, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, cudaStream_t s);
 
-enum : int { CLIP_SMALL = 0, CLIP_MEDIUM = 1, CLIP_LARGE = 2 };  // table capacities of the clip kernel (clip.cu)
+// table capacities of the clip kernel (clip.cu); CLIP_SMALL_FAST = the small configuration without the serial walk:
+// cells that need it come back flagged like cells that ran out of table and are redone by CLIP_SMALL
+enum : int { CLIP_SMALL = 0, CLIP_MEDIUM = 1, CLIP_LARGE = 2, CLIP_SMALL_FAST = 3 };
 void launch_clip(const ClipParams& p, int tier, cudaStream_t s);
 uint32_t clip_medium_fmax();
 uint32_t clip_medium_vmax();
