@@ -214,6 +214,32 @@ def test_parallel_cut_equals_serial_walk(tess, gen, tmp_path):
         assert np.array_equal(outs["par"][k], outs["sweep"][k]), k
 
 
+@pytest.mark.xfail(reason="TESS_FAST_MAIN_PASS was written after the round's GPU budget was spent: emulator-verified and timed once, "
+                          "but this comparison has never run on a GPU; an XPASS here is the signal to make it the default", strict=False)
+def test_fast_main_pass_is_bit_identical(tess, gen, tmp_path):
+    """TESS_FAST_MAIN_PASS=1 runs the main pass with the instantiation that has no serial walk (and no divergence
+    guards); cells that need the walk are handed back and redone by the instantiation that has it.  Random, clustered
+    and exact-lattice input (where every cell is handed back) must come out bit-identical, work counters included."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, importlib, numpy as np; sys.path.insert(0, %r);"
+        "T = importlib.import_module('the-tessellator_b200'); G = T.generators;"
+        "pts = np.concatenate([G.uniform(150000, 5), 0.25 + 0.5 * G.simple_cubic(12), G.clustered(60000, 4, k=4)]);"
+        "d = T.Diagram(0); d.add_particles(pts); d.initialize(T.Polyhedron(0, 0, 0, 1, 1, 1));"
+        "b = d.compute_all_cells(outputs=7 | 16); c = b.counters();"
+        "np.savez(sys.argv[1], v=b.volumes, n=b.neighbors, a=b.areas, o=b.face_offsets, s=b.status, c=np.array([c[k] for k in sorted(c)], dtype=np.uint64))"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("default", {}), ("fast", {"TESS_FAST_MAIN_PASS": "1"})):
+        f = str(tmp_path / f"{tag}.npz")
+        subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, **env))
+        outs[tag] = np.load(f)
+    for k in "vnaosc":
+        assert np.array_equal(outs["default"][k], outs["fast"][k]), k
+
+
 # ------------------------------------------------------------------ options ------------------
 def test_reference_radius_mode(tess, gen, ob):
     pts = gen.uniform(20_000, 57)
