@@ -223,6 +223,13 @@ int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t i
 int tess_result_timings(const tess_result* r, double ms[4]);
 /* ms[0] = binning pass (histogram + scan + scatter + gather) of the last initialize. */
 int tess_diagram_timings(const tess_diagram* d, double ms[1]);
+/* Which kernel runs the main clip pass (process-wide; a tuning and test knob, not part of the reference's API):
+ * -1 default (thread per cell; warp per cell for geometry output and query cells), 0 warp per cell with the serial walk,
+ * 3 warp per cell without it, 4 thread per cell.  Results are bit-identical for every choice.  The environment variable
+ * TESS_MAIN_TIER=thread|fast|small sets the initial value. */
+int tess_set_main_tier(int tier);
+/* stats[0] = tier that ran the main pass of this result, stats[1..3] = cells redone by the wider-table / medium / large passes. */
+int tess_result_tier_stats(const tess_result* r, uint64_t stats[4]);
 /* Number of CUDA kernels this library has launched in this process so far. */
 uint64_t tess_kernel_launch_count(void);
 /* Measures the device's FP64 FMA throughput with a register-resident DFMA loop (a denominator for

@@ -701,6 +701,9 @@ CellResult Diagram::compute(const Vec3& position, OptIdx self, SearchMode mode, 
             }
     }
     r.max_radius_sq = polyhedron.max_vertex_radius_sq();
+    r.pool_slots[0] = static_cast<uint32_t>(polyhedron.vertices.len());
+    r.pool_slots[1] = static_cast<uint32_t>(polyhedron.edges.len());
+    r.pool_slots[2] = static_cast<uint32_t>(polyhedron.faces.len());
     r.counters.vertex_classifications = polyhedron.counters.vertex_classifications;
     r.counters.cuts = polyhedron.counters.cuts;
     r.counters.new_vertices = polyhedron.counters.new_vertices;

@@ -384,6 +384,7 @@ struct CellResult {
     std::vector<Vec3> face_loop_vertices;   // the loops, concatenated: compute_face_vertices (polyhedron.rs:897-919)
     uint32_t status = 0;
     double max_radius_sq = 0;        // final max |v|^2
+    uint32_t pool_slots[3] = {0, 0, 0};  // slots ever used by the vertex / half-edge / face pools (Pool::len): capacity the cell needed
     CellCounters counters;
 };
 

@@ -16,6 +16,7 @@ static void emu_launch_kernel(void (*entry)(const void*), const void* arg, unsig
 }
 
 #include "../../the-tessellator_b200/csrc/clip.cu"
+#include "../../the-tessellator_b200/csrc/clip_thread.cu"
 
 namespace tess {
 void note_launch(int) {}
@@ -137,7 +138,7 @@ int emu_clip_run(emu_clip_args* a) {
     g_blocks = a->blocks ? a->blocks : g_os_threads;
     g_reverse = a->reverse != 0;
     g_collectives = 0;
-    launch_clip(P, a->large, nullptr);  // 0 small, 1 medium, 2 large (tess::CLIP_*)
+    launch_clip(P, a->large, nullptr);  // 0 small, 1 medium, 2 large, 3 small without the serial walk, 4 thread per cell (tess::CLIP_*)
     if (a->counters)
         for (int i = 0; i < CNT_N; ++i) a->counters[i] = counters[i];
     a->collectives = g_collectives;

@@ -81,6 +81,7 @@ inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 inline unsigned __brev(unsigned v) {
     unsigned r = 0;
     for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);

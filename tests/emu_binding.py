@@ -113,9 +113,9 @@ class EmuGrid:
              query_xyz=None, want_vertices=False, count=True):
         """count=False runs the instantiation without work counters (the one the product times)."""
         L = lib()
-        tier = {False: 0, True: 2, "medium": 1, "fast": 3}[large]  # tess::CLIP_SMALL / CLIP_LARGE / CLIP_MEDIUM / CLIP_SMALL_FAST
+        tier = {False: 0, True: 2, "medium": 1, "fast": 3, "thread": 4}[large]  # tess::CLIP_SMALL / CLIP_LARGE / CLIP_MEDIUM / CLIP_SMALL_FAST / CLIP_THREAD
         if fstride is None:
-            fstride = (40, int(L.emu_medium_fmax()), int(L.emu_large_fmax()), 40)[tier]
+            fstride = (40, int(L.emu_medium_fmax()), int(L.emu_large_fmax()), 40, 40)[tier]
         ws = None if work_slots is None else np.ascontiguousarray(work_slots, np.uint32)
         m = self.n if ws is None else ws.size
         q = None
@@ -134,7 +134,7 @@ class EmuGrid:
         a.work_slots, a.n_work, a.query_xyz = (None if ws is None else ws.ctypes.data), m, (None if q is None else q.ctypes.data)
         geo = None
         if want_vertices:
-            vmax = (64, 256, 1024, 64)[tier]
+            vmax = (64, 256, 1024, 64, 64)[tier]
             geo = dict(gv=np.zeros((m * vmax, 3)), gl=np.zeros(m * 3 * vmax, np.uint32), cur=np.zeros(2, np.uint64), nv=np.zeros(m, np.uint32),
                        nl=np.zeros(m, np.uint32), vb=np.zeros(m, np.uint64), lb=np.zeros(m, np.uint64), fl=np.zeros(m * fstride, np.uint16))
             a.gv_xyz, a.gl_idx, a.gv_cap, a.gl_cap = geo["gv"].ctypes.data, geo["gl"].ctypes.data, m * vmax, m * 3 * vmax

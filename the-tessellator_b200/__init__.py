@@ -1,7 +1,7 @@
 """the-tessellator_b200 — B200-native per-particle Voronoi cell construction.
 
 One hot path of mcomstock/the-tessellator, rebuilt for sm_100a: GPU counting-sort binning
-(celery.rs) + warp-per-cell half-space clipping (polyhedron.rs) behind the reference's
+(celery.rs) + thread-per-cell / warp-per-cell half-space clipping (polyhedron.rs) behind the reference's
 Diagram / Cell / VoronoiFace API (interface.rs).  See DESIGN.md.
 
 The directory name contains a hyphen; import it with
@@ -9,6 +9,6 @@ The directory name contains a hyphen; import it with
 """
 from . import _lib, generators  # noqa: F401
 from ._lib import TessError, build  # noqa: F401
-from .interface import Cell, CellBatch, Diagram, Polyhedron, VoronoiFace, device_count  # noqa: F401
+from .interface import Cell, CellBatch, Diagram, Polyhedron, VoronoiFace, device_count, set_main_tier  # noqa: F401
 
-__all__ = ["Diagram", "Cell", "VoronoiFace", "Polyhedron", "CellBatch", "TessError", "build", "device_count", "generators"]
+__all__ = ["Diagram", "Cell", "VoronoiFace", "Polyhedron", "CellBatch", "TessError", "build", "device_count", "set_main_tier", "generators"]

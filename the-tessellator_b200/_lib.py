@@ -33,7 +33,7 @@ SYMBOLS = (
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
     "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs",
     "tess_find_neighbors", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
-    "tess_result_download", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
+    "tess_result_download", "tess_set_main_tier", "tess_result_tier_stats", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
 
 
@@ -132,6 +132,8 @@ def lib() -> C.CDLL:
     for n in ("tess_query_offsets", "tess_query_indices", "tess_query_status"):
         sig(n, ci, vp, P(vp))
     sig("tess_kernel_launch_count", u64)
+    sig("tess_set_main_tier", ci, ci)
+    sig("tess_result_tier_stats", ci, vp, P(u64 * 4))
     sig("tess_result_timings", ci, vp, P(f64 * 4))
     sig("tess_diagram_timings", ci, vp, P(f64 * 1))
     sig("tess_measure_fp64_peak", ci, ci, P(f64))

@@ -9,6 +9,7 @@
 //     |i|,|j|,|k| <= R and to keys strictly below min_axis sq(R*size) so that it is an exact
 //     prefix of the reference's full (2cpd-1)^3 table, ordered canonically by (key, i, j, k).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -213,6 +214,7 @@ struct tess_result {
     unsigned long long* counters = nullptr;
     unsigned long long counters_redo[CNT_N] = {0, 0, 0, 0, 0, 0, 0, 0};  // work done by the large-cell pass
     double ms_clip = 0, ms_redo = 0, ms_outputs = 0, ms_total = 0;  // CUDA-event durations on the launching stream
+    uint64_t tier_stats[4] = {0, 0, 0, 0};  // main tier (CLIP_*), cells redone by pass A / B / C
     // host copies
     std::vector<double> h_vol, h_area, h_vtx;
     std::vector<uint64_t> h_offsets, h_voffsets, h_fv_offsets;
@@ -582,6 +584,21 @@ struct HostSink {
     int n_chunks;
 };
 
+// tess_set_main_tier / TESS_MAIN_TIER (thread | fast | small): which kernel runs the main clip pass; -1 = the default choice
+std::atomic<int> g_main_tier{-2};  // -2: not set, read the environment
+int forced_main_tier() {
+    int t = g_main_tier.load(std::memory_order_relaxed);
+    if (t != -2) return t;
+    t = -1;
+    if (const char* e = std::getenv("TESS_MAIN_TIER")) {
+        const std::string v(e);
+        if (v == "thread") t = CLIP_THREAD;
+        else if (v == "fast") t = CLIP_SMALL_FAST;
+        else if (v == "small") t = CLIP_SMALL;
+    }
+    return t;
+}
+
 int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* query_host, size_t n_query, tess_result** out, const HostSink* sink = nullptr) {
     tess_opts o;
     if (opts_in) o = *opts_in; else tess_opts_default(&o);
@@ -682,10 +699,17 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
     P.flags = (std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u) | (std::getenv("TESS_FORCE_SWEEP") ? 2u : 0u);
-    // A/B switch (off by default, not yet timed on a GPU): run the main pass with the instantiation that has no serial
-    // walk and no divergence guards (clip.cu, CLIP_SMALL_FAST); cells that need the walk come back flagged like cells
-    // that ran out of table and take redo pass A, which has it.  Query cells are never redone, so they keep CLIP_SMALL.
-    const int main_tier = (std::getenv("TESS_FAST_MAIN_PASS") && !query) ? CLIP_SMALL_FAST : CLIP_SMALL;
+    // Main pass: one thread per cell (clip_thread.cu) for cells of the diagram's own particles; what its tables cannot hold,
+    // and cells that need the reference-shaped serial walk, come back flagged like cells that ran out of search table and
+    // take redo pass A (the warp-per-cell kernel with the walk).  Geometry output is written by the warp-per-cell kernels
+    // only (CLIP_SMALL_FAST: no serial walk, no divergence guards; leftovers likewise to pass A).  Query cells are computed
+    // by CLIP_SMALL and, like every main pass's leftovers, redone tier by tier.  tess_set_main_tier / TESS_MAIN_TIER override.
+    int main_tier = query ? CLIP_SMALL : (want_vtx ? CLIP_SMALL_FAST : CLIP_THREAD);
+    {
+        const int forced = forced_main_tier();
+        if (forced == CLIP_SMALL || forced == CLIP_SMALL_FAST || (forced == CLIP_THREAD && !query && !want_vtx)) main_tier = forced;
+    }
+    r->tier_stats[0] = (uint64_t)main_tier;
     // ---- the pipeline ------------------------------------------------------------------------------
     // The rows are computed in C chunks (C = 1 unless the results stream to host buffers,
     // tess_compute_all_to_host).  Per chunk: clip its cells in sorted (spatial) order; redo what the
@@ -959,6 +983,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
         if (rc != TESS_OK) return rc;
     }
     r->n_faces = total;
+    r->tier_stats[1] = total_redo_a; r->tier_stats[2] = total_redo_b; r->tier_stats[3] = total_redo_c;
     if (std::getenv("TESS_TRACE") && (total_redo_a || total_redo_b))
         std::fprintf(stderr, "[tess trace] redo: pass A (wider table) re-ran %u cells, pass B (medium cells) %u, pass C (large cells) %u, final R=%d\n", total_redo_a, total_redo_b,
                      total_redo_c, final_R);
@@ -1141,6 +1166,18 @@ int tess_result_download(const tess_result* r, double* volumes, uint64_t* face_o
 }
 
 uint64_t tess_kernel_launch_count(void) { return launch_count(); }
+
+int tess_set_main_tier(int tier) {
+    if (tier != -1 && tier != CLIP_SMALL && tier != CLIP_SMALL_FAST && tier != CLIP_THREAD) return fail(TESS_ERR_INVALID, "tess_set_main_tier: -1 (default), 0 (warp per cell), 3 (warp per cell, no serial walk) or 4 (thread per cell)");
+    g_main_tier.store(tier == -1 ? -2 : tier, std::memory_order_relaxed);
+    return TESS_OK;
+}
+
+int tess_result_tier_stats(const tess_result* r, uint64_t stats[4]) {
+    if (!r || !stats) return fail(TESS_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < 4; ++i) stats[i] = r->tier_stats[i];
+    return TESS_OK;
+}
 
 int tess_result_timings(const tess_result* r, double ms[4]) {
     if (!r || !ms) return fail(TESS_ERR_INVALID, "NULL argument");

@@ -26,9 +26,11 @@
 //     vertex Outside (n.v - |r|/2 <= |v| - |r|/2 <= 0 < tol), i.e. find_outgoing_edge
 //     (polyhedron.rs:399-410) would have returned None for them: results are unchanged.
 #include <algorithm>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
+#include "cube_tables.cuh"
 #include "tess_math.cuh"
 
 namespace tess {
@@ -45,14 +47,6 @@ constexpr uint32_t FULL = 0xffffffffu;
 #define TESS_UNIFORM_BEGIN(ptr, bytes) ((void)0)
 #define TESS_UNIFORM_END() ((void)0)
 #endif
-
-// Start cube: {flip, target, next} of the 24 half-edges (ids of polyhedron.rs:97-199)
-__constant__ uint32_t kCubeEdges[24] = {0x100301u, 0x0f0002u, 0x140103u, 0x050200u, 0x110205u, 0x030106u, 0x170507u, 0x090604u,
-                                        0x120609u, 0x07050au, 0x16040bu, 0x0d0708u, 0x13070du, 0x0b040eu, 0x15000fu, 0x01030cu,
-                                        0x000211u, 0x040612u, 0x080713u, 0x0c0310u, 0x020015u, 0x0e0416u, 0x0a0517u, 0x060114u};
-
-// ... and, per cube vertex, the three half-edges that START there (source(e) = target(flip(e)))
-__constant__ unsigned char kCubeVout[24] = {2, 15, 21, 3, 6, 20, 0, 5, 17, 1, 12, 16, 11, 14, 22, 7, 10, 23, 4, 9, 18, 8, 13, 19};
 
 // ---------------------------------------------------------------------------------------------
 // Bit masks over table slots.  Small cells keep them in registers, large cells in shared memory.
@@ -1474,15 +1468,29 @@ void launch_cfg(const ClipParams& p, cudaStream_t s) {
     *p.work_counter = 0u;
     emu_launch_kernel([](const void* a) { clip_kernel<Cfg, COUNT, SERIAL>(*static_cast<const ClipParams*>(a)); }, &p, Cfg::WARPS * 32, smem);
 #else
-    static bool configured = false;
-    static int per_sm_cached = 0, sms_cached = 0;
-    if (!configured) {
-        TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg, COUNT, SERIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        TESS_CUDA_CHECK(cudaGetDevice(&dev));
-        TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev));
-        TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_cached, clip_kernel<Cfg, COUNT, SERIAL>, Cfg::WARPS * 32, smem));
-        configured = true;
+    // Per device: the dynamic shared-memory opt-in, the SM count and the occupancy belong to the device the launch goes
+    // to, and tess_compute_* may run on several host threads at once (tess.h).
+    struct DevCfg {
+        bool configured = false;
+        int per_sm = 0, sms = 0;
+    };
+    static DevCfg cfgs[64];
+    static std::mutex cfg_mutex;
+    int dev = 0;
+    TESS_CUDA_CHECK(cudaGetDevice(&dev));
+    int sms_cached = 0, per_sm_cached = 0;
+    {
+        std::lock_guard<std::mutex> lock(cfg_mutex);
+        DevCfg local;
+        DevCfg& c = (dev >= 0 && dev < 64) ? cfgs[dev] : local;
+        if (!c.configured) {
+            TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_kernel<Cfg, COUNT, SERIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TESS_CUDA_CHECK(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+            TESS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, clip_kernel<Cfg, COUNT, SERIAL>, Cfg::WARPS * 32, smem));
+            c.configured = true;
+        }
+        sms_cached = c.sms;
+        per_sm_cached = c.per_sm;
     }
     int sms = sms_cached, per_sm = per_sm_cached;
     if (per_sm < 1) per_sm = 1;
@@ -1504,6 +1512,8 @@ void launch_clip(const ClipParams& p, int tier, cudaStream_t s) {
         if (count) launch_cfg<LargeCfg, true>(p, s); else launch_cfg<LargeCfg, false>(p, s);
     } else if (tier == CLIP_MEDIUM) {
         if (count) launch_cfg<MediumCfg, true>(p, s); else launch_cfg<MediumCfg, false>(p, s);
+    } else if (tier == CLIP_THREAD) {
+        launch_clip_thread(p, s);
     } else if (tier == CLIP_SMALL_FAST) {
         if (count) launch_cfg<SmallCfg, true, false>(p, s); else launch_cfg<SmallCfg, false, false>(p, s);
     } else {

@@ -145,8 +145,13 @@ void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base,
 
 // table capacities of the clip kernel (clip.cu); CLIP_SMALL_FAST = the small configuration without the serial walk:
 // cells that need it come back flagged like cells that ran out of table and are redone by CLIP_SMALL
-enum : int { CLIP_SMALL = 0, CLIP_MEDIUM = 1, CLIP_LARGE = 2, CLIP_SMALL_FAST = 3 };
+// CLIP_THREAD = one thread per cell with tables for the common cell (clip_thread.cu); what it cannot finish is handed back
+// the same way
+enum : int { CLIP_SMALL = 0, CLIP_MEDIUM = 1, CLIP_LARGE = 2, CLIP_SMALL_FAST = 3, CLIP_THREAD = 4 };
 void launch_clip(const ClipParams& p, int tier, cudaStream_t s);
+void launch_clip_thread(const ClipParams& p, cudaStream_t s);
+uint32_t clip_thread_fmax();
+uint32_t clip_thread_vmax();
 uint32_t clip_medium_fmax();
 uint32_t clip_medium_vmax();
 uint32_t clip_small_fmax();

@@ -136,6 +136,12 @@ class CellBatch:
         check(_lib.lib().tess_result_timings(self._h, C.byref(arr)))
         return dict(clip_ms=arr[0], redo_ms=arr[1], outputs_ms=arr[2], total_ms=arr[3])
 
+    def tier_stats(self) -> dict:
+        """Which kernel ran the main clip pass and how many cells the redo passes took over."""
+        arr = (C.c_uint64 * 4)()
+        check(_lib.lib().tess_result_tier_stats(self._h, C.byref(arr)))
+        return dict(main_tier=MAIN_TIERS.get(int(arr[0]), str(int(arr[0]))), redo_a=int(arr[1]), redo_b=int(arr[2]), redo_c=int(arr[3]))
+
     def download(self, volumes=None, face_offsets=None, neighbors=None, areas=None, status=None, stream: int = 0) -> None:
         """Asynchronous copies into caller-owned (ideally pinned) host arrays; the caller synchronises."""
         ptr = lambda a: None if a is None else a.ctypes.data if hasattr(a, "ctypes") else a.data_ptr()  # noqa: E731
@@ -474,6 +480,16 @@ class VoronoiFace:
     def compute_vertices(self) -> np.ndarray:
         """interface.rs:403-405: the face's vertices in loop order, cell-local coordinates."""
         return self.cell._batch.face_vertices(self.cell._row, self._k).copy()
+
+
+MAIN_TIERS = {0: "small", 3: "fast", 4: "thread"}
+
+
+def set_main_tier(tier) -> None:
+    """Kernel of the main clip pass: None / "default", "thread" (one thread per cell), "fast" (one warp per cell, no serial
+    walk) or "small" (one warp per cell with the reference-shaped serial walk).  Results are bit-identical for every choice."""
+    code = {None: -1, "default": -1, "small": 0, "fast": 3, "thread": 4}[tier]
+    check(_lib.lib().tess_set_main_tier(code))
 
 
 def device_count() -> int:
