@@ -29,6 +29,20 @@ def _diagram(tess, pts, box=BOX, groups=None):
     return d
 
 
+# The main clip pass has three kernels (tess_set_main_tier) and each has two instantiations (with / without the work
+# counters, outputs & 16): bench.py times "no counters" on the default tier.  Every oracle comparison below runs on all
+# of them: (tier, outputs).
+VARIANTS = [("default", ALL_OUT), ("default", 7), ("small", ALL_OUT), ("small", 7), ("fast", ALL_OUT), ("fast", 7), ("thread", ALL_OUT), ("thread", 7)]
+
+
+@pytest.fixture(params=VARIANTS, ids=lambda v: f"{v[0]}-{'count' if v[1] & 16 else 'nocount'}")
+def variant(request, tess):
+    tier, outputs = request.param
+    tess.set_main_tier(tier)
+    yield tier, outputs
+    tess.set_main_tier("default")
+
+
 def test_device_and_library(tess):
     assert tess.device_count() >= 1
     assert os.path.exists(tess._lib.LIB_PATH)
@@ -87,16 +101,18 @@ class _Gold:
 
 
 @pytest.mark.parametrize("name", FIXTURES)
-def test_cells_match_golden_fixture(tess, gen, name):
+def test_cells_match_golden_fixture(tess, gen, name, variant):
+    tier, outputs = variant
     g = np.load(os.path.join(GOLD, name))
     pts, box = _fixture_points(name, gen, g)
     d = _diagram(tess, pts, box)
     # the fixtures come from the oracle's FULL search table: give the GPU the full table too, so that
     # even the work counters must agree (the default R=8 table + redo pass is covered below)
-    b = d.compute_all_cells(outputs=ALL_OUT, table_radius=1 << 20)
+    b = d.compute_all_cells(outputs=outputs, table_radius=1 << 20)
     helpers.assert_cells_match(b, _Gold(g), area_rtol=0.0, vol_rtol=0.0, what=name)  # rtol 0: equal values
-    c = b.counters()
-    assert [c[k] for k in CNAMES] == g["counters"].tolist()
+    if outputs & 16:
+        c = b.counters()
+        assert [c[k] for k in CNAMES] == g["counters"].tolist()
     if "status" in g.files:
         assert np.array_equal(b.status, g["status"])  # degenerate skips flagged on the same cells
     else:
@@ -106,7 +122,8 @@ def test_cells_match_golden_fixture(tess, gen, name):
 
 # ------------------------------------------------------------------ cells vs live oracle ----
 @pytest.mark.parametrize("case", ["uniform200k", "clustered100k", "bcc16k", "tiny"])
-def test_cells_match_oracle(tess, gen, ob, case):
+def test_cells_match_oracle(tess, gen, ob, case, variant):
+    tier, outputs = variant
     pts = {
         "uniform200k": lambda: gen.uniform(200_000, 51),
         "clustered100k": lambda: gen.clustered(100_000, 4, k=8),
@@ -114,7 +131,9 @@ def test_cells_match_oracle(tess, gen, ob, case):
         "tiny": lambda: gen.uniform(5, 52),
     }[case]()
     d = _diagram(tess, pts)
-    b = d.compute_all_cells(outputs=ALL_OUT)
+    b = d.compute_all_cells(outputs=outputs)
+    if tier != "default":
+        assert b.tier_stats()["main_tier"] == tier
     r = ob.Diagram(pts, box=BOX, table_radius=8).compute_cells(mode=ob.MODE_SECURITY)
     ok = r.status == 0  # cells the oracle's own truncated table could finish
     assert ok.mean() > 0.99
@@ -122,7 +141,7 @@ def test_cells_match_oracle(tess, gen, ob, case):
     assert np.all(b.status == 0)  # the GPU re-runs table-exhausted cells with a larger table
     assert abs(b.volumes.sum() - 1.0) <= 1e-12
     assert abs(b.volume_sum() - 1.0) <= 1e-12
-    if ok.all():
+    if ok.all() and outputs & 16:
         c = b.counters()
         for k in ("tested", "vertex_classifications", "cuts", "new_vertices", "faces", "visited", "table_entries"):
             if case == "clustered100k" and k in ("visited", "table_entries", "tested", "vertex_classifications", "cuts", "new_vertices"):
@@ -144,19 +163,19 @@ class _Subset:
         self.areas = np.asarray(r.areas)[sel]
 
 
-def test_exhausted_table_is_redone_not_wrong(tess, gen, ob):
+def test_exhausted_table_is_redone_not_wrong(tess, gen, ob, variant):
     """A deliberately tiny shell table (R=1) cannot terminate any cell; the redo pass with larger
     tables must still deliver the exact cells."""
     pts = gen.uniform(20_000, 53)
     d = _diagram(tess, pts)
-    b = d.compute_all_cells(outputs=ALL_OUT, table_radius=1)
+    b = d.compute_all_cells(outputs=variant[1], table_radius=1)
     r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
     helpers.assert_cells_identical(b, r, what="R=1")
     assert np.all(b.status == 0)
     d.close()
 
 
-def test_large_cell_path(tess, gen, ob):
+def test_large_cell_path(tess, gen, ob, variant):
     """A particle surrounded by a dense shell has hundreds of faces: more than the small tables
     hold (64 vertices / 40 faces), so it must come from the large-cell configuration
     (1024 vertices / 512 faces; beyond that the cell is reported with TESS_STATUS_CAPACITY_OVERFLOW)."""
@@ -165,7 +184,7 @@ def test_large_cell_path(tess, gen, ob):
     shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
     pts = np.concatenate([[[0.5, 0.5, 0.5]], shell, gen.uniform(2000, 55)[np.linalg.norm(gen.uniform(2000, 55) - 0.5, axis=1) > 0.35]])
     d = _diagram(tess, pts)
-    b = d.compute_all_cells(outputs=ALL_OUT)
+    b = d.compute_all_cells(outputs=variant[1])
     r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
     assert len(r.cell_neighbors(0)) > 100
     helpers.assert_cells_identical(b, r, what="shell")
@@ -214,30 +233,30 @@ def test_parallel_cut_equals_serial_walk(tess, gen, tmp_path):
         assert np.array_equal(outs["par"][k], outs["sweep"][k]), k
 
 
-@pytest.mark.xfail(reason="TESS_FAST_MAIN_PASS was written after the round's GPU budget was spent: emulator-verified and timed once, "
-                          "but this comparison has never run on a GPU; an XPASS here is the signal to make it the default", strict=False)
-def test_fast_main_pass_is_bit_identical(tess, gen, tmp_path):
-    """TESS_FAST_MAIN_PASS=1 runs the main pass with the instantiation that has no serial walk (and no divergence
-    guards); cells that need the walk are handed back and redone by the instantiation that has it.  Random, clustered
-    and exact-lattice input (where every cell is handed back) must come out bit-identical, work counters included."""
-    import subprocess
-    import sys
-
-    code = (
-        "import sys, importlib, numpy as np; sys.path.insert(0, %r);"
-        "T = importlib.import_module('the-tessellator_b200'); G = T.generators;"
-        "pts = np.concatenate([G.uniform(150000, 5), 0.25 + 0.5 * G.simple_cubic(12), G.clustered(60000, 4, k=4)]);"
-        "d = T.Diagram(0); d.add_particles(pts); d.initialize(T.Polyhedron(0, 0, 0, 1, 1, 1));"
-        "b = d.compute_all_cells(outputs=7 | 16); c = b.counters();"
-        "np.savez(sys.argv[1], v=b.volumes, n=b.neighbors, a=b.areas, o=b.face_offsets, s=b.status, c=np.array([c[k] for k in sorted(c)], dtype=np.uint64))"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+def test_main_tiers_are_bit_identical(tess, gen):
+    """The three kernels of the main pass (warp per cell with the serial walk / without it / thread per cell) hand what
+    they cannot finish to the next tier.  Random, clustered and exact-lattice input (where nearly every cell is handed
+    back) must come out bit-identical from all of them, work counters included."""
+    G = gen
+    pts = np.concatenate([G.uniform(150000, 5), 0.25 + 0.5 * G.simple_cubic(12), G.clustered(60000, 4, k=4)])
+    d = _diagram(tess, pts)
     outs = {}
-    for tag, env in (("default", {}), ("fast", {"TESS_FAST_MAIN_PASS": "1"})):
-        f = str(tmp_path / f"{tag}.npz")
-        subprocess.check_call([sys.executable, "-c", code, f], env=dict(os.environ, **env))
-        outs[tag] = np.load(f)
-    for k in "vnaosc":
-        assert np.array_equal(outs["default"][k], outs["fast"][k]), k
+    try:
+        for tier in ("small", "fast", "thread"):
+            tess.set_main_tier(tier)
+            b = d.compute_all_cells(outputs=7 | 16)
+            assert b.tier_stats()["main_tier"] == tier
+            c = b.counters()
+            outs[tier] = (b.volumes.copy(), b.neighbors.copy(), b.areas.copy(), b.face_offsets.copy(), b.status.copy(), [c[k] for k in sorted(c)])
+            b2 = d.compute_all_cells(outputs=7)
+            for x, y in zip(outs[tier][:5], (b2.volumes, b2.neighbors, b2.areas, b2.face_offsets, b2.status)):
+                assert np.array_equal(x, y), tier
+    finally:
+        tess.set_main_tier("default")
+    for tier in ("fast", "thread"):
+        for k, (x, y) in enumerate(zip(outs["small"], outs[tier])):
+            assert np.array_equal(x, y), (tier, k)
+    d.close()
 
 
 # ------------------------------------------------------------------ options ------------------
@@ -409,10 +428,20 @@ def test_slab_decomposition_is_bit_identical(tess, gen):
 
 
 # ------------------------------------------------------------------ full-size configs --------
-def _full_size_checks(tess, gen, ob, pts, sample_seed, n_sample):
-    d = _diagram(tess, pts)
+def _full_size_checks(tess, gen, ob, pts, sample_seed, n_sample, box=BOX):
+    d = _diagram(tess, pts, box)
     b = d.compute_all_cells(outputs=ALL_OUT)
     n = len(pts)
+    # the instantiations bench.py times (no counters), on every main tier, must give the same arrays bit for bit
+    try:
+        for tier in ("default", "small", "fast", "thread"):
+            tess.set_main_tier(tier)
+            t = d.compute_all_cells(outputs=7)
+            for name in ("volumes", "face_offsets", "neighbors", "areas", "status"):
+                assert np.array_equal(getattr(t, name), getattr(b, name)), (tier, name)
+            del t
+    finally:
+        tess.set_main_tier("default")
     assert np.all(b.status == 0)
     assert abs(b.volume_sum() - 1.0) <= 1e-12
     assert abs(float(np.sum(b.volumes)) - 1.0) <= 1e-12
@@ -468,7 +497,7 @@ def test_vertices_and_face_loops_match_oracle(tess, gen, ob):
 
 # ------------------------------------------------------------------ awkward inputs -----------
 @pytest.mark.parametrize("case", ["duplicates", "on_walls", "outside_box", "two_points", "collinear", "coplanar", "lattice_jitter0"])
-def test_awkward_inputs_match_oracle(tess, gen, ob, case):
+def test_awkward_inputs_match_oracle(tess, gen, ob, case, variant):
     """Inputs the reference does not guard against (exact duplicates give a NaN plane that cuts nothing,
     SURVEY D16; particles on or outside the container; exact lattice ties).  Whatever the reference's
     arithmetic does with them, the kernel must do the same, bit for bit, and flag the same cells."""
@@ -483,13 +512,14 @@ def test_awkward_inputs_match_oracle(tess, gen, ob, case):
         "lattice_jitter0": lambda: gen.bcc(6, 5, jitter=0.0),
     }[case]()
     d = _diagram(tess, pts)
-    b = d.compute_all_cells(outputs=ALL_OUT, table_radius=1 << 20)
+    b = d.compute_all_cells(outputs=variant[1], table_radius=1 << 20)
     r = ob.Diagram(pts, box=BOX).compute_cells(mode=ob.MODE_SECURITY)
     helpers.assert_cells_identical(b, r, what=case)
     assert np.array_equal(b.status, r.status)
-    c = b.counters()
-    for k in ("tested", "cuts", "new_vertices", "faces", "degenerate_skips"):
-        assert c[k] == r.counters[k], k
+    if variant[1] & 16:
+        c = b.counters()
+        for k in ("tested", "cuts", "new_vertices", "faces", "degenerate_skips"):
+            assert c[k] == r.counters[k], k
     d.close()
 
 

@@ -699,15 +699,15 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;
     P.flags = (std::getenv("TESS_FORCE_SERIAL") ? 1u : 0u) | (std::getenv("TESS_FORCE_SWEEP") ? 2u : 0u);
-    // Main pass: one thread per cell (clip_thread.cu) for cells of the diagram's own particles; what its tables cannot hold,
-    // and cells that need the reference-shaped serial walk, come back flagged like cells that ran out of search table and
-    // take redo pass A (the warp-per-cell kernel with the walk).  Geometry output is written by the warp-per-cell kernels
-    // only (CLIP_SMALL_FAST: no serial walk, no divergence guards; leftovers likewise to pass A).  Query cells are computed
-    // by CLIP_SMALL and, like every main pass's leftovers, redone tier by tier.  tess_set_main_tier / TESS_MAIN_TIER override.
-    int main_tier = query ? CLIP_SMALL : (want_vtx ? CLIP_SMALL_FAST : CLIP_THREAD);
+    // Main pass: the warp-per-cell kernel without the serial walk and without divergence guards (CLIP_SMALL_FAST); cells
+    // that need the reference-shaped serial walk come back flagged like cells that ran out of search table and take redo
+    // pass A (CLIP_SMALL, which has the walk).  CLIP_THREAD (one thread per cell, clip_thread.cu) hands back the same way
+    // what its tables cannot hold; it writes no geometry output and builds no query cells.  Query cells are computed by
+    // CLIP_SMALL and, like every main pass's leftovers, redone tier by tier.  tess_set_main_tier / TESS_MAIN_TIER override.
+    int main_tier = query ? CLIP_SMALL : CLIP_SMALL_FAST;
     {
         const int forced = forced_main_tier();
-        if (forced == CLIP_SMALL || forced == CLIP_SMALL_FAST || (forced == CLIP_THREAD && !query && !want_vtx)) main_tier = forced;
+        if (forced == CLIP_SMALL || (forced == CLIP_SMALL_FAST && !query) || (forced == CLIP_THREAD && !query && !want_vtx)) main_tier = forced;
     }
     r->tier_stats[0] = (uint64_t)main_tier;
     // ---- the pipeline ------------------------------------------------------------------------------
