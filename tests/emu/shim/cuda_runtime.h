@@ -72,6 +72,9 @@ inline double4 make_double4(double x, double y, double z, double w) { return dou
 #define __match_any_sync(m, v) emu::match_any((m), (uint64_t)(v), __LINE__)
 #define __syncwarp() emu::syncwarp(__LINE__)
 #define __syncthreads() emu::syncthreads(__LINE__)
+// a spin-wait gives the other warps of the block their turn
+#define __nanosleep(ns) emu::yield_to_scheduler()
+#define __threadfence_block() ((void)0)
 // static shared arrays: one block at a time runs on a host thread
 #define __shared__ static thread_local
 

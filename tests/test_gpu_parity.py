@@ -132,8 +132,8 @@ def test_cells_match_oracle(tess, gen, ob, case, variant):
     }[case]()
     d = _diagram(tess, pts)
     b = d.compute_all_cells(outputs=outputs)
-    if tier != "default":
-        assert b.tier_stats()["main_tier"] == tier
+    if tier != "default":  # (the thread-per-cell kernel keeps no work counters: with counters the default kernel runs)
+        assert b.tier_stats()["main_tier"] == ("fast" if tier == "thread" and outputs & 16 else tier)
     r = ob.Diagram(pts, box=BOX, table_radius=8).compute_cells(mode=ob.MODE_SECURITY)
     ok = r.status == 0  # cells the oracle's own truncated table could finish
     assert ok.mean() > 0.99
@@ -245,10 +245,13 @@ def test_main_tiers_are_bit_identical(tess, gen):
         for tier in ("small", "fast", "thread"):
             tess.set_main_tier(tier)
             b = d.compute_all_cells(outputs=7 | 16)
-            assert b.tier_stats()["main_tier"] == tier
+            assert b.tier_stats()["main_tier"] == ("fast" if tier == "thread" else tier)  # no work counters in the thread-per-cell kernel
             c = b.counters()
             outs[tier] = (b.volumes.copy(), b.neighbors.copy(), b.areas.copy(), b.face_offsets.copy(), b.status.copy(), [c[k] for k in sorted(c)])
             b2 = d.compute_all_cells(outputs=7)
+            assert b2.tier_stats()["main_tier"] == tier
+            if tier == "thread":
+                assert 0 < b2.tier_stats()["redo_a"] < len(pts) // 4  # it hands back what its tables cannot hold, and only that
             for x, y in zip(outs[tier][:5], (b2.volumes, b2.neighbors, b2.areas, b2.face_offsets, b2.status)):
                 assert np.array_equal(x, y), tier
     finally:

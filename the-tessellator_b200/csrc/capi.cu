@@ -702,12 +702,12 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     // Main pass: the warp-per-cell kernel without the serial walk and without divergence guards (CLIP_SMALL_FAST); cells
     // that need the reference-shaped serial walk come back flagged like cells that ran out of search table and take redo
     // pass A (CLIP_SMALL, which has the walk).  CLIP_THREAD (one thread per cell, clip_thread.cu) hands back the same way
-    // what its tables cannot hold; it writes no geometry output and builds no query cells.  Query cells are computed by
+    // what its tables cannot hold; it writes no geometry output, keeps no work counters and builds no query cells.  Query cells are computed by
     // CLIP_SMALL and, like every main pass's leftovers, redone tier by tier.  tess_set_main_tier / TESS_MAIN_TIER override.
     int main_tier = query ? CLIP_SMALL : CLIP_SMALL_FAST;
     {
         const int forced = forced_main_tier();
-        if (forced == CLIP_SMALL || (forced == CLIP_SMALL_FAST && !query) || (forced == CLIP_THREAD && !query && !want_vtx)) main_tier = forced;
+        if (forced == CLIP_SMALL || (forced == CLIP_SMALL_FAST && !query) || (forced == CLIP_THREAD && !query && !want_vtx && !want_cnt)) main_tier = forced;
     }
     r->tier_stats[0] = (uint64_t)main_tier;
     // ---- the pipeline ------------------------------------------------------------------------------

@@ -17,13 +17,22 @@
 //     which IS pool.rs's LIFO free list (pool.rs:85-121), so slot numbers — and with them find_outgoing_edge's
 //     "first edge in slot order", every face's starting edge, the face order, the fan anchors and the
 //     summation orders — are the reference's, and volumes / areas come out bit-identical to the CPU oracle.
-//   * Tables are sized for the common cell (45 vertices / 140 half-edges / 24 faces = 1805 B per thread:
-//     128 threads fill the SM's 227 KB).  A cell that outgrows them, meets a vertex ON a plane (the
-//     reference's Incident case, polyhedron.rs:555-565) or runs out of search table is handed back through
+//   * Tables are sized for the common cell (44 vertices / 136 half-edges / 24 faces = 1764 B per thread:
+//     128 cell-building threads fill the SM's 227 KB).  A cell that outgrows them, meets a vertex ON a plane
+//     (the reference's Incident case, polyhedron.rs:555-565) or runs out of search table is handed back through
 //     the failed-cell list and redone by the warp-per-cell kernel, like every other tier's leftovers.
-//   * Divergence is managed, not avoided: each lane is a small state machine (fetch a candidate / classify /
-//     cut / results) and the warp runs a phase when enough lanes wait for it (cuts and results are batched,
-//     fetch + classify run for whoever needs them).
+//   * The search is NOT done by the thread that builds the cell.  First version (profiles/r02_thread_kernel.md):
+//     every lane walked its own search table — three dependent global loads per grid cell with one warp per
+//     scheduler to hide them, and lanes that need 1 or 100 table steps to find their next candidate in the same
+//     loop: 4.8 of 32 lanes active, 142 ms per 10^6 cells.  Now the CTA is warp-specialised: 4 CONSUMER warps
+//     (thread per cell) and PW PRODUCER warps.  A producer serves one consumer lane at a time with all 32 lanes:
+//     32 search-table entries per step (coalesced), their grid cells' particle runs, |r|^2 against the consumer's
+//     published threshold, survivors compacted IN TABLE ORDER into that lane's ring of candidate slots in shared
+//     memory.  The published threshold may be stale — it only ever shrinks, so a stale one lets through a superset;
+//     the consumer re-tests every candidate against its own threshold, and a candidate beyond the reference's
+//     stopping entry has |r|^2 >= key > threshold: the tested sequence is exactly the reference's.
+//   * Divergence is managed, not avoided: each consumer lane is a small state machine (take a candidate /
+//     classify / cut / results) and the warp runs a phase when enough lanes wait for it.
 //   * arithmetic is tess_math.cuh's, operation for operation the reference's.
 #include <algorithm>
 
@@ -44,11 +53,22 @@ constexpr uint32_t TFULL = 0xffffffffu;
 #define TESS_T_DONE_MIN 8  // finished cells waiting before the results phase runs
 #endif
 
+#ifndef TESS_T_PWARPS
+#define TESS_T_PWARPS 8    // producer warps per CTA (each serves 128 / PW consumer lanes)
+#endif
+#ifndef TESS_T_TRIES
+#define TESS_T_TRIES 2     // candidates a lane may take (and reject) per round
+#endif
+
 struct ThreadCfg {
-    static constexpr int V = 45, E = 140, F = 24;
-    static constexpr int WARPS = 4;
+    static constexpr int V = 44, E = 136, F = 24;
+    static constexpr int WARPS = 4;                 // consumer warps: one thread per cell
+    static constexpr int PWARPS = TESS_T_PWARPS;    // producer warps
+    static constexpr int LPP = 32 * WARPS / PWARPS; // consumer lanes per producer warp
+    static constexpr int QD = 8;                    // ring of candidate slots per consumer lane
     static constexpr uint32_t NONE = 0xFFu;
 };
+static_assert(ThreadCfg::LPP >= 1 && ThreadCfg::LPP <= 32 && ThreadCfg::LPP * ThreadCfg::PWARPS == 32 * ThreadCfg::WARPS, "producer warps must divide the consumer lanes");
 
 // The tables of the 32 cells of one warp, lane-interleaved.
 struct __align__(16) ThreadTables {
@@ -58,7 +78,41 @@ struct __align__(16) ThreadTables {
     uint8_t vedge[ThreadCfg::V][32];   // one half-edge that starts at the vertex (the others: next(flip(e)) twice)
     uint8_t fstart[ThreadCfg::F][32];  // Face.starting_edge_index; free face slots are chained through it
 };
-static_assert(sizeof(ThreadTables) * ThreadCfg::WARPS <= 232448, "four warps of tables must fit the 227 KB of one SM");
+
+// What producers and consumers exchange, per consumer thread c (0..127).  Ring items: a sorted slot (< 2^31), or
+// Q_HALO | table index (the entry touches a plane this rank does not hold), or Q_END / Q_END_EXH (end of the walk: a key
+// above the threshold / the end of a table that does not cover the grid).
+struct __align__(16) ThreadShared {
+    ThreadTables tab[ThreadCfg::WARPS];
+    double thr[32 * ThreadCfg::WARPS];              // consumer -> producer: current threshold (4 max|v|^2, or the caller's radius); -2: stop now
+    uint32_t q[ThreadCfg::QD][32 * ThreadCfg::WARPS];
+    uint32_t head[32 * ThreadCfg::WARPS];           // items taken (consumer), items published (producer): free-running counters
+    uint32_t tail[32 * ThreadCfg::WARPS];
+    uint32_t cell[32 * ThreadCfg::WARPS];           // consumer -> producer: sorted slot of the cell under construction / C_IDLE / C_EXIT
+};
+static_assert(sizeof(ThreadShared) <= 232448, "tables and rings must fit the 227 KB of one SM");
+constexpr uint32_t Q_END = 0xFFFFFFFFu, Q_END_EXH = 0xFFFFFFFEu, Q_HALO = 0x80000000u;
+constexpr uint32_t C_EXIT = 0xFFFFFFFFu, C_IDLE = 0xFFFFFFFEu;
+
+// release / acquire on shared-memory words (CTA scope)
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+#ifdef TESS_WARP_EMU
+    *reinterpret_cast<volatile uint32_t*>(p) = v;
+#else
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+#ifdef TESS_WARP_EMU
+    return *reinterpret_cast<const volatile uint32_t*>(p);
+#else
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+__device__ __forceinline__ void st_volatile_f64(double* p, double v) { *reinterpret_cast<volatile double*>(p) = v; }
 
 constexpr uint32_t WALL0 = 0xFFFFFFF0u;
 
@@ -309,46 +363,231 @@ __device__ int thread_cut(TMesh& M, const Plane& pl, uint32_t nbr_ref, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------
-// The kernel: persistent warps; every lane pulls cells from the work counter.
+// Producer: ExpandingSearch::expand_all_* (celery.rs:971-1075) for the cells of LPP consumer lanes, 32 search-table
+// entries per step.  Lane j (< LPP) keeps the cursor of consumer thread c0 + j in its registers.
 // ---------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(ThreadCfg::WARPS * 32, 1) clip_thread_kernel(const ClipParams P) {
+__device__ void producer_warp(const ClipParams& P, ThreadShared* S, const int pw, const int lane) {
+    const GridSpec& G = P.grid;
+    const int cpd = (int)G.cpd;
+    const bool radius_mode = !(P.search_radius != P.search_radius);  // not NaN
+    const int c = pw * ThreadCfg::LPP + (lane < ThreadCfg::LPP ? lane : 0);  // the consumer thread this lane keeps the cursor of
+    const bool serving = lane < ThreadCfg::LPP;
+    uint32_t cell_seen = C_IDLE, ti = 0, off = 0, tail = 0;
+    bool walk_done = true;
+    double px = 0, py = 0, pz = 0;
+    int hx = 0, hy = 0, hz = 0;
+
+    for (;;) {
+        // ---- who needs candidates --------------------------------------------------------------------
+        bool gone = true, want = false;
+        uint32_t room = 0;
+        if (serving) {
+            const uint32_t cs = ld_acquire(&S->cell[c]);
+            if (cs != C_EXIT) {
+                gone = false;
+                if (cs != cell_seen && cs != C_IDLE) {
+                    // a new cell (ExpandingSearch::new, celery.rs:882-902: home cell of the position)
+                    cell_seen = cs;
+                    const double2* q = reinterpret_cast<const double2*>(P.sorted + cs);
+                    const double2 a = __ldg(q);
+                    px = a.x; py = a.y; pz = __ldg(reinterpret_cast<const double*>(q + 1));
+                    hx = (int)axis_index(px, G.xmin, G.xmax, G.ix, G.cpd);
+                    hy = (int)axis_index(py, G.ymin, G.ymax, G.iy, G.cpd);
+                    hz = (int)axis_index(pz, G.zmin, G.zmax, G.iz, G.cpd);
+                    ti = 0; off = 0;
+                    walk_done = false;
+                }
+                if (!walk_done) {
+                    room = (uint32_t)ThreadCfg::QD - (tail - ld_acquire(&S->head[c]));
+                    want = room >= (uint32_t)ThreadCfg::QD / 2u;
+                }
+            }
+        }
+        if (__all_sync(TFULL, gone)) break;
+        uint32_t need = __ballot_sync(TFULL, want);
+        if (!need) {
+            __nanosleep(40);
+            continue;
+        }
+        // ---- one step of the walk for each of them -----------------------------------------------------
+        while (need) {
+            const int j = __ffs((int)need) - 1;
+            need &= need - 1u;
+            const int cj = pw * ThreadCfg::LPP + j;
+            const uint32_t ti0 = __shfl_sync(TFULL, ti, j), off0 = __shfl_sync(TFULL, off, j), tail0 = __shfl_sync(TFULL, tail, j);
+            const uint32_t room0 = __shfl_sync(TFULL, room, j), self = __shfl_sync(TFULL, cell_seen, j);
+            const double qx = __shfl_sync(TFULL, px, j), qy = __shfl_sync(TFULL, py, j), qz = __shfl_sync(TFULL, pz, j);
+            const int h0 = __shfl_sync(TFULL, hx, j), h1 = __shfl_sync(TFULL, hy, j), h2 = __shfl_sync(TFULL, hz, j);
+            const double thr = ld_volatile_f64(&S->thr[cj]);
+            // lane i looks at table entry ti0 + i; the walk stops at the first entry whose key exceeds the threshold
+            // (celery.rs:1036) or at the end of the table
+            const uint32_t e_idx = ti0 + (uint32_t)lane;
+            const bool in_table = e_idx < P.table_len;
+            ShellEntry e;
+            e.key = 0.0; e.di = e.dj = e.dk = e.pad = 0;
+            if (in_table) e = P.table[e_idx];
+            const uint32_t stopmask = __ballot_sync(TFULL, !in_table || e.key > thr);
+            int s_lane = stopmask ? __ffs((int)stopmask) - 1 : 32;
+            uint32_t cur = 0, end = 0;
+            bool halo = false;
+            if (lane < s_lane) {
+                const int gx = h0 + e.di, gy = h1 + e.dj, gz = h2 + e.dk;
+                if (!(gx < 0 || gx >= cpd || gy < 0 || gy >= cpd || gz < 0 || gz >= cpd)) {
+                    if (gx < (int)G.local_lo || gx >= (int)G.local_hi) {
+                        halo = true;  // a plane this rank does not hold
+                    } else {
+                        const uint32_t gc = ((uint32_t)(gx - (int)G.local_lo) * G.cpd + (uint32_t)gy) * G.cpd + (uint32_t)gz;
+                        cur = __ldg(P.delim + gc);
+                        end = __ldg(P.delim + gc + 1);
+                    }
+                }
+                if (lane == 0) cur = (end - cur > off0) ? cur + off0 : end;  // the part of the first entry's run already handed over
+            }
+            // at most 32 particles of a run per step: the step ends with the first longer run
+            const bool longrun = end - cur > 32u;
+            if (longrun) end = cur + 32u;
+            const uint32_t longmask = __ballot_sync(TFULL, longrun);
+            const int l_lane = longmask ? __ffs((int)longmask) - 1 : 32;  // (< s_lane: lanes from s_lane on have empty runs)
+            if (lane > l_lane) {
+                end = cur;
+                halo = false;
+            }
+            // interface.rs:280-312 for the particles of the run: self, group, then (security mode) |r|^2 against the threshold
+            uint32_t pass = 0;
+            for (uint32_t k = 0; cur + k < end; ++k) {
+                const uint32_t slot = cur + k;
+                if (slot == self) continue;       // interface.rs:283/301 (by index)
+                if (P.target_group != -1)         // interface.rs:284/293 (-2: no particle carries the requested group)
+                    if (!(P.target_group >= 0 && P.groups_sorted[slot] == (uint64_t)P.target_group)) continue;
+                if (!radius_mode) {
+                    const double2* cq = reinterpret_cast<const double2*>(P.sorted + slot);
+                    const double2 a = __ldg(cq);
+                    const double zz = __ldg(reinterpret_cast<const double*>(cq + 1));
+                    const double rx = subd(a.x, qx), ry = subd(a.y, qy), rz = subd(zz, qz);  // interface.rs:322-326
+                    if (dot3(rx, ry, rz, rx, ry, rz) >= thr) continue;  // cannot have a vertex Outside (header of clip.cu)
+                }
+                pass |= 1u << k;
+            }
+            // items of this step in table order: per entry, its halo marker or its surviving particles; then the end marker
+            const bool ends = l_lane == 32 && s_lane < 32;  // the walk ends inside this step
+            uint32_t cnt = (uint32_t)__popc(pass) + (halo ? 1u : 0u);
+            if (ends && lane == s_lane) cnt = 1u;
+            uint32_t pre = cnt;  // inclusive scan
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(TFULL, pre, d);
+                if (lane >= d) pre += o;
+            }
+            const uint32_t total = __shfl_sync(TFULL, pre, 31);
+            pre -= cnt;
+            const uint32_t emit = pre >= room0 ? 0u : (cnt < room0 - pre ? cnt : room0 - pre);
+            {
+                uint32_t m = pass;
+                for (uint32_t r = 0; r < emit; ++r) {
+                    uint32_t item;
+                    if (ends && lane == s_lane) item = (in_table || P.table_full || radius_mode) ? Q_END : Q_END_EXH;
+                    else if (halo) item = Q_HALO | e_idx;
+                    else {
+                        item = cur + (uint32_t)__ffs((int)m) - 1u;
+                        m &= m - 1u;
+                    }
+                    S->q[(tail0 + pre + r) % (uint32_t)ThreadCfg::QD][cj] = item;
+                }
+            }
+            // where the next step starts: the first entry that could not hand over everything, else the first long run,
+            // else after the 32 entries (or nowhere: the end marker is out)
+            const uint32_t partmask = __ballot_sync(TFULL, emit < cnt);
+            uint32_t n_ti, n_off;
+            bool n_done = false;
+            if (partmask) {
+                const int i = __ffs((int)partmask) - 1;
+                // particles of entry i's run up to and including the last one handed over
+                uint32_t used = 0;
+                if (lane == i && emit > 0u && !halo && !(ends && lane == s_lane)) {
+                    uint32_t m = pass;
+                    for (uint32_t r = 1; r < emit; ++r) m &= m - 1u;
+                    used = (uint32_t)__ffs((int)m);  // position of the emit-th survivor + 1
+                }
+                used = __shfl_sync(TFULL, used, i);
+                n_ti = ti0 + (uint32_t)i;
+                n_off = (i == 0 ? off0 : 0u) + used;
+            } else if (l_lane < 32 && l_lane < s_lane) {
+                n_ti = ti0 + (uint32_t)l_lane;
+                n_off = (l_lane == 0 ? off0 : 0u) + 32u;
+            } else if (ends) {
+                n_ti = ti0;
+                n_off = 0;
+                n_done = true;
+            } else {
+                n_ti = ti0 + 32u;
+                n_off = 0;
+            }
+            const uint32_t n_tail = tail0 + (total < room0 ? total : room0);
+            __syncwarp();
+            if (lane == j) {
+                ti = n_ti; off = n_off; walk_done = n_done; tail = n_tail;
+                st_release(&S->tail[cj], n_tail);  // the items written above (by all lanes, ordered by the __syncwarp) become visible with it
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel: persistent CTAs, one per SM; every consumer lane pulls cells from the work counter.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1) clip_thread_kernel(const ClipParams P) {
 #ifdef TESS_WARP_EMU  // tests/emu: this source run lane by lane on the CPU (test infrastructure only)
     unsigned char* smem_raw = emu::dynamic_smem();
 #else
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
+    ThreadShared* S = reinterpret_cast<ThreadShared*>(smem_raw);
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32 * ThreadCfg::WARPS) {
+        S->head[threadIdx.x] = 0u;
+        S->tail[threadIdx.x] = 0u;
+        S->cell[threadIdx.x] = C_IDLE;
+        S->thr[threadIdx.x] = -2.0;
+    }
+    __syncthreads();
+    if (warp >= ThreadCfg::WARPS) {
+        producer_warp(P, S, warp - ThreadCfg::WARPS, lane);
+        return;
+    }
+
+    // ---- consumer ------------------------------------------------------------------------------------
+    const int c = (int)threadIdx.x;
     const uint32_t lt = (1u << lane) - 1u;
     TMesh M;
-    M.t = reinterpret_cast<ThreadTables*>(smem_raw) + (threadIdx.x >> 5);
+    M.t = &S->tab[warp];
     M.lane = lane;
     M.vlive = 0ull;
     M.flive = 0u;
     M.e_head = M.f_head = ThreadCfg::NONE;
     M.e_hwm = M.e_nfree = M.f_hwm = 0u;
-
-    const GridSpec& G = P.grid;
-    const int cpd = (int)G.cpd;
     const bool radius_mode = !(P.search_radius != P.search_radius);  // not NaN
-    unsigned long long t_vis = 0, t_test = 0, t_vc = 0, t_cuts = 0, t_nv = 0, t_tab = 0, t_faces = 0;
+    const double last_key = P.table_len ? P.table[P.table_len - 1].key : -1.0;
 
     // ---- per-lane state of the cell under construction ------------------------------------------
     int state = S_NEW;
-    uint32_t work = 0, self_slot = 0xFFFFFFFFu, status = 0;
+    uint32_t work = 0, self_slot = 0xFFFFFFFFu, status = 0, head = 0;
     bool failed = false;
     double px = 0, py = 0, pz = 0;
-    int hx = 0, hy = 0, hz = 0;
-    uint32_t ti = 0, cur = 0, end = 0;       // next search_order entry; particles of the current entry still to visit
     double stop_thr = 0.0;                   // 4 * max|v|^2, or the caller's radius
     uint32_t far_v = 0;                      // the vertex that attains max|v|^2
+    // the staged ring item: taken from the ring (and its position requested) ahead of its use
+    bool staged = false;
+    uint32_t st_item = 0;
+    double sx = 0, sy = 0, sz = 0;
     double rx = 0, ry = 0, rz = 0, r2 = 0;   // the candidate handed to the classification
     uint32_t cand_slot = 0;
     Plane pl = {0, 0, 0, 0};
     unsigned long long in = 0, out = 0;
-    uint32_t c_vis = 0, c_test = 0, c_vc = 0, c_cuts = 0, c_nv = 0, c_tab = 0;
+    uint32_t c_nv = 0;
 
     for (;;) {
+        bool progressed = false;
         // ---- claim the next cells (one atomic per warp) and set up their start polyhedra -------------
         const uint32_t need = __ballot_sync(TFULL, state == S_NEW);
         if (need) {
@@ -360,6 +599,7 @@ __global__ void __launch_bounds__(ThreadCfg::WARPS * 32, 1) clip_thread_kernel(c
                 work = base + (uint32_t)__popc(need & lt);
                 if (work >= P.n_work) {
                     state = S_EXIT;
+                    st_release(&S->cell[c], C_EXIT);
                 } else {
                     // the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207)
                     self_slot = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
@@ -367,131 +607,40 @@ __global__ void __launch_bounds__(ThreadCfg::WARPS * 32, 1) clip_thread_kernel(c
                     const double2 a = __ldg(q), b = __ldg(q + 1);
                     px = a.x; py = a.y; pz = b.x;
                     M.build_cube(P.box, px, py, pz);
-                    // ExpandingSearch::new (celery.rs:882-902): home cell of the position
-                    hx = (int)axis_index(px, G.xmin, G.xmax, G.ix, G.cpd);
-                    hy = (int)axis_index(py, G.ymin, G.ymax, G.iy, G.cpd);
-                    hz = (int)axis_index(pz, G.zmin, G.zmax, G.iz, G.cpd);
                     status = 0;
                     failed = false;
-                    ti = 0; cur = 0; end = 0;
                     const double rmax2 = M.max_radius_sq(far_v);
                     // security mode compares table keys AND |r|^2 with 4*max|v|^2; reference-radius mode compares table
                     // keys with the caller's radius (celery.rs:1036) and rejects nothing
                     stop_thr = radius_mode ? P.search_radius : mul(4.0, rmax2);
-                    c_vis = c_test = c_vc = c_cuts = c_nv = c_tab = 0;
+                    st_volatile_f64(&S->thr[c], stop_thr);
+                    st_release(&S->cell[c], self_slot);  // the producer starts this cell's walk
                     state = S_FETCH;
+                    progressed = true;
                 }
             }
         }
         if (__all_sync(TFULL, state == S_EXIT)) break;
 
-        // ---- fetch: walk the search order until a candidate has to be tested (celery.rs:981-1014 /
-        //      interface.rs:280-312) ------------------------------------------------------------------
-        if (state == S_FETCH) {
-            for (;;) {
-                if (cur < end) {
-                    const uint32_t slot = cur++;
-                    if (COUNT) ++c_vis;
-                    if (slot == self_slot) continue;  // interface.rs:283/301 (by index)
-                    if (P.target_group != -1)         // interface.rs:284/293 (-2: no particle carries the requested group)
-                        if (!(P.target_group >= 0 && P.groups_sorted[slot] == (uint64_t)P.target_group)) continue;
-                    const double2* cq = reinterpret_cast<const double2*>(P.sorted + slot);
-                    const double2 a = __ldg(cq);
-                    const double zz = __ldg(reinterpret_cast<const double*>(cq + 1));
-                    // interface.rs:322-326: search point - position
-                    rx = subd(a.x, px); ry = subd(a.y, py); rz = subd(zz, pz);
-                    r2 = dot3(rx, ry, rz, rx, ry, rz);
-                    if (!radius_mode && r2 >= stop_thr) continue;  // cannot have a vertex Outside (header of clip.cu)
-                    cand_slot = slot;
-                    if (COUNT) ++c_test;
-                    state = S_TEST;
-                    break;
-                }
-                if (ti >= P.table_len) {
-                    if (!P.table_full && !radius_mode) {
-                        status |= ST_TABLE_EXHAUSTED;
-                        failed = true;
-                    }
-                    state = S_DONE;
-                    break;
-                }
-                const ShellEntry e = P.table[ti];
-                if (e.key > stop_thr) {  // the walk stops at the first entry whose key exceeds the threshold (celery.rs:1036)
-                    state = S_DONE;
-                    break;
-                }
-                ++ti;
-                if (COUNT) ++c_tab;
-                const int gx = hx + e.di, gy = hy + e.dj, gz = hz + e.dk;
-                if (gx < 0 || gx >= cpd || gy < 0 || gy >= cpd || gz < 0 || gz >= cpd) continue;
-                if (gx < (int)G.local_lo || gx >= (int)G.local_hi) {
-                    status |= ST_HALO_INSUFFICIENT;  // a plane this rank does not hold
-                    continue;
-                }
-                const uint32_t c = ((uint32_t)(gx - (int)G.local_lo) * G.cpd + (uint32_t)gy) * G.cpd + (uint32_t)gz;
-                cur = __ldg(P.delim + c);
-                end = __ldg(P.delim + c + 1);
-            }
-        }
-
-        // ---- classify every live vertex against the candidate's bisector plane (find_outgoing_edge's vertex scan,
-        //      polyhedron.rs:399-405, and every later vector_location call of the walk) ------------------
-        if (state == S_TEST) {
-            {
-                // Plane::halfway_from_origin_to (vector3.rs:223-225); mag_sq(rel) is r2
-                const double m = __dsqrt_rn(r2);
-                const double inv = __ddiv_rn(1.0, m);
-                pl.nx = mul(rx, inv); pl.ny = mul(ry, inv); pl.nz = mul(rz, inv);
-                pl.off = dot3(pl.nx, pl.ny, pl.nz, mul(rx, 0.5), mul(ry, 0.5), mul(rz, 0.5));
-            }
-            uint32_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
-            const int top = 64 - __clzll((long long)M.vlive);  // slots above the highest live one are not read
-#pragma unroll
-            for (int j = 0; j < ThreadCfg::V; ++j) {
-                if ((j & 3) == 0 && j >= top) break;
-                const double sd = signed_distance(pl, M.t->vx[j][lane], M.t->vy[j][lane], M.t->vz[j][lane]);
-                if (j < 32) {
-                    if (sd < -TESS_TOL) in_lo |= 1u << j;   // vector3.rs:173
-                    if (sd > TESS_TOL) out_lo |= 1u << j;   // vector3.rs:171
-                } else {
-                    if (sd < -TESS_TOL) in_hi |= 1u << (j - 32);
-                    if (sd > TESS_TOL) out_hi |= 1u << (j - 32);
-                }
-            }
-            in = (((unsigned long long)in_hi << 32) | in_lo) & M.vlive;  // dead slots hold stale coordinates
-            out = (((unsigned long long)out_hi << 32) | out_lo) & M.vlive;
-            if (COUNT) c_vc += (uint32_t)__popcll(M.vlive);
-            if (out == 0ull) {
-                state = S_FETCH;  // polyhedron.rs:408-410: no cut
-            } else if ((M.vlive & ~in & ~out) != 0ull) {
-                // a vertex ON the plane: the reference destroys it and re-creates it as a copy (polyhedron.rs:555-565),
-                // after which vertices are no longer 3-valent — the warp-per-cell kernel's serial walk does that
-                status |= ST_TABLE_EXHAUSTED;
-                failed = true;
-                state = S_DONE;
-            } else {
-                state = S_CUT;
-            }
-        }
-
         // ---- cut: when enough lanes wait for it, or nobody can do anything else --------------------------
         {
             const uint32_t m_cut = __ballot_sync(TFULL, state == S_CUT);
-            const uint32_t m_fetch = __ballot_sync(TFULL, state == S_FETCH);
-            if (m_cut && (__popc(m_cut) >= TESS_T_CUT_MIN || m_fetch == 0u)) {
+            const uint32_t m_can = __ballot_sync(TFULL, state == S_FETCH && (staged || ld_acquire(&S->tail[c]) != head));
+            if (m_cut && (__popc(m_cut) >= TESS_T_CUT_MIN || m_can == 0u)) {
                 if (state == S_CUT) {
+                    progressed = true;
                     const int rc = thread_cut(M, pl, cand_slot, in, out, c_nv);
                     if (rc != TCUT_OK) {
                         status |= ST_TABLE_EXHAUSTED;  // handed back: redone by the warp-per-cell kernel
                         failed = true;
-                        state = S_DONE;
-                    } else {
-                        ++c_cuts;
+                        st_volatile_f64(&S->thr[c], -2.0);  // every key exceeds it: the producer sends the end marker
+                    } else if (!radius_mode && ((out >> far_v) & 1ull)) {
                         // the farthest vertex only ever moves inwards: new vertices lie between an Outside and an Inside
                         // one, so max|v|^2 changes only when the vertex that attained it was cut off
-                        if (!radius_mode && (COUNT || ((out >> far_v) & 1ull))) stop_thr = mul(4.0, M.max_radius_sq(far_v));
-                        state = S_FETCH;
+                        stop_thr = mul(4.0, M.max_radius_sq(far_v));
+                        st_volatile_f64(&S->thr[c], stop_thr);
                     }
+                    state = S_FETCH;
                 }
             }
         }
@@ -499,9 +648,10 @@ __global__ void __launch_bounds__(ThreadCfg::WARPS * 32, 1) clip_thread_kernel(c
         // ---- results: weighted normals, areas, volume, neighbours ------------------------------------
         {
             const uint32_t m_done = __ballot_sync(TFULL, state == S_DONE);
-            const uint32_t m_busy = __ballot_sync(TFULL, state == S_FETCH || state == S_CUT);
+            const uint32_t m_busy = __ballot_sync(TFULL, state == S_CUT || (state == S_FETCH && (staged || ld_acquire(&S->tail[c]) != head)));
             if (m_done && (__popc(m_done) >= TESS_T_DONE_MIN || m_busy == 0u)) {
                 if (state == S_DONE) {
+                    progressed = true;
                     const long long self_id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + self_slot) + 3));
                     const size_t row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
                     const size_t srow = P.stage_by_work ? (size_t)work : row;
@@ -558,44 +708,119 @@ __global__ void __launch_bounds__(ThreadCfg::WARPS * 32, 1) clip_thread_kernel(c
                     P.nfaces[row] = failed ? 0u : nf;
                     P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
                     if (P.cell_id) P.cell_id[row] = self_id;
-                    if (COUNT && !failed) {  // only cells this pass finished are counted; the others are counted by the redo pass
-                        t_vis += c_vis; t_test += c_test; t_vc += c_vc; t_cuts += c_cuts; t_nv += c_nv; t_tab += c_tab; t_faces += nf;
-                    }
                     state = S_NEW;
                 }
             }
         }
-    }
 
-    if (COUNT && P.counters) {
-        atomicAdd(&P.counters[CNT_VISITED], t_vis);
-        atomicAdd(&P.counters[CNT_TESTED], t_test);
-        atomicAdd(&P.counters[CNT_VC], t_vc);
-        atomicAdd(&P.counters[CNT_CUTS], t_cuts);
-        atomicAdd(&P.counters[CNT_NV], t_nv);
-        atomicAdd(&P.counters[CNT_TABLE], t_tab);
-        atomicAdd(&P.counters[CNT_FACES], t_faces);
+        // ---- take candidates from the ring (interface.rs:280-312 in the producer's order) ------------------
+#pragma unroll 1
+        for (int tries = 0; tries <= TESS_T_TRIES; ++tries) {
+            // stage the next item; a particle's position is requested now and used a phase later
+            if (!staged && state != S_EXIT && state != S_NEW && state != S_DONE) {
+                if (ld_acquire(&S->tail[c]) != head) {
+                    st_item = S->q[head % (uint32_t)ThreadCfg::QD][c];
+                    ++head;
+                    st_release(&S->head[c], head);
+                    staged = true;
+                    progressed = true;
+                    if (st_item < Q_HALO) {
+                        const double2* cq = reinterpret_cast<const double2*>(P.sorted + st_item);
+                        const double2 a = __ldg(cq);
+                        sx = a.x; sy = a.y;
+                        sz = __ldg(reinterpret_cast<const double*>(cq + 1));
+                    }
+                }
+            }
+            if (tries == TESS_T_TRIES) break;
+            if (state == S_FETCH && staged) {
+                staged = false;
+                progressed = true;
+                if (st_item >= Q_END_EXH) {
+                    // the end of the walk; a table that ended before a key exceeded the threshold has to be widened
+                    // (keys ascend: no key exceeded it iff the last one does not)
+                    if (st_item == Q_END_EXH && !failed && !(last_key > stop_thr)) {
+                        status |= ST_TABLE_EXHAUSTED;
+                        failed = true;
+                    }
+                    state = S_DONE;
+                } else if (failed) {
+                    // a cell that was handed back only drains its ring
+                } else if (st_item >= Q_HALO) {
+                    // reached by the reference's walk iff its key is within the threshold as of now (keys ascend, thresholds shrink)
+                    if (radius_mode || !(P.table[st_item & 0x7FFFFFFFu].key > stop_thr)) status |= ST_HALO_INSUFFICIENT;
+                } else {
+                    rx = subd(sx, px); ry = subd(sy, py); rz = subd(sz, pz);  // interface.rs:322-326: search point - position
+                    r2 = dot3(rx, ry, rz, rx, ry, rz);
+                    if (radius_mode || r2 < stop_thr) {  // else: cannot have a vertex Outside (header of clip.cu)
+                        cand_slot = st_item;
+                        state = S_TEST;
+                    }
+                }
+            }
+        }
+
+        // ---- classify every live vertex against the candidate's bisector plane (find_outgoing_edge's vertex scan,
+        //      polyhedron.rs:399-405, and every later vector_location call of the walk) ------------------
+        if (state == S_TEST) {
+            {
+                // Plane::halfway_from_origin_to (vector3.rs:223-225); mag_sq(rel) is r2
+                const double m = __dsqrt_rn(r2);
+                const double inv = __ddiv_rn(1.0, m);
+                pl.nx = mul(rx, inv); pl.ny = mul(ry, inv); pl.nz = mul(rz, inv);
+                pl.off = dot3(pl.nx, pl.ny, pl.nz, mul(rx, 0.5), mul(ry, 0.5), mul(rz, 0.5));
+            }
+            uint32_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
+            const int top = 64 - __clzll((long long)M.vlive);  // slots above the highest live one are not read
+#pragma unroll
+            for (int j = 0; j < ThreadCfg::V; ++j) {
+                if ((j & 3) == 0 && j >= top) break;
+                const double sd = signed_distance(pl, M.t->vx[j][lane], M.t->vy[j][lane], M.t->vz[j][lane]);
+                if (j < 32) {
+                    if (sd < -TESS_TOL) in_lo |= 1u << j;   // vector3.rs:173
+                    if (sd > TESS_TOL) out_lo |= 1u << j;   // vector3.rs:171
+                } else {
+                    if (sd < -TESS_TOL) in_hi |= 1u << (j - 32);
+                    if (sd > TESS_TOL) out_hi |= 1u << (j - 32);
+                }
+            }
+            in = (((unsigned long long)in_hi << 32) | in_lo) & M.vlive;  // dead slots hold stale coordinates
+            out = (((unsigned long long)out_hi << 32) | out_lo) & M.vlive;
+            if (out == 0ull) {
+                state = S_FETCH;  // polyhedron.rs:408-410: no cut
+            } else if ((M.vlive & ~in & ~out) != 0ull) {
+                // a vertex ON the plane: the reference destroys it and re-creates it as a copy (polyhedron.rs:555-565),
+                // after which vertices are no longer 3-valent — the warp-per-cell kernel's serial walk does that
+                status |= ST_TABLE_EXHAUSTED;
+                failed = true;
+                st_volatile_f64(&S->thr[c], -2.0);
+                state = S_FETCH;  // drains the ring up to the end marker
+            } else {
+                state = S_CUT;
+            }
+        }
+        if (!__any_sync(TFULL, progressed)) __nanosleep(20);
     }
 }
 
-template <bool COUNT>
 void launch_thread_cfg(const ClipParams& p, cudaStream_t s) {
     if (!p.n_work) return;
-    const size_t smem = sizeof(ThreadTables) * ThreadCfg::WARPS;
+    const size_t smem = sizeof(ThreadShared);
+    const int threads = 32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS);
 #ifdef TESS_WARP_EMU
     *p.work_counter = 0u;
-    emu_launch_kernel([](const void* a) { clip_thread_kernel<COUNT>(*static_cast<const ClipParams*>(a)); }, &p, ThreadCfg::WARPS * 32, smem);
+    emu_launch_kernel([](const void* a) { clip_thread_kernel(*static_cast<const ClipParams*>(a)); }, &p, threads, smem);
 #else
     int dev = 0, sms = 0;
     TESS_CUDA_CHECK(cudaGetDevice(&dev));
     TESS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // (set on every launch: the attribute is per device and this is one driver call next to a multi-millisecond kernel)
-    TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_thread_kernel<COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent grid: one CTA of four warps per SM (its tables fill the SM's shared memory)
+    TESS_CUDA_CHECK(cudaFuncSetAttribute(clip_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent grid: one CTA per SM (its tables fill the SM's shared memory)
     const unsigned int want = (unsigned int)((p.n_work + ThreadCfg::WARPS * 32 - 1) / (ThreadCfg::WARPS * 32));
     const unsigned int grid = std::min<unsigned int>(want, (unsigned int)sms);
     TESS_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s));
-    clip_thread_kernel<COUNT><<<grid, ThreadCfg::WARPS * 32, smem, s>>>(p);
+    clip_thread_kernel<<<grid, threads, smem, s>>>(p);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 #endif
@@ -604,10 +829,8 @@ void launch_thread_cfg(const ClipParams& p, cudaStream_t s) {
 }  // namespace
 
 // Preconditions (the host checks them, capi.cu): cells of the diagram's own particles (no query positions), no
-// geometry output.  fstride >= 24.
-void launch_clip_thread(const ClipParams& p, cudaStream_t s) {
-    if (p.counters) launch_thread_cfg<true>(p, s); else launch_thread_cfg<false>(p, s);
-}
+// geometry output, no work counters.  fstride >= 24.
+void launch_clip_thread(const ClipParams& p, cudaStream_t s) { launch_thread_cfg(p, s); }
 uint32_t clip_thread_vmax() { return ThreadCfg::V; }
 uint32_t clip_thread_fmax() { return ThreadCfg::F; }
 
