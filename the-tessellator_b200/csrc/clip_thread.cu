@@ -35,6 +35,7 @@
 //     classify / cut / results) and the warp runs a phase when enough lanes wait for it.
 //   * arithmetic is tess_math.cuh's, operation for operation the reference's.
 #include <algorithm>
+#include <cstdio>
 
 #include "common.cuh"
 #include "cube_tables.cuh"
@@ -49,12 +50,21 @@ constexpr uint32_t TFULL = 0xffffffffu;
 #ifndef TESS_T_CUT_MIN
 #define TESS_T_CUT_MIN 24  // lanes with a cut pending before the cut phase runs (unless nobody can do anything else)
 #endif
+#ifndef TESS_T_TEST_MIN
+#define TESS_T_TEST_MIN 20 // lanes with a candidate in hand before the classification phase runs
+#endif
+#ifndef TESS_T_SPINS
+#define TESS_T_SPINS 2     // short sleeps a warp takes for starved lanes before it runs a phase below its threshold
+#endif
 #ifndef TESS_T_DONE_MIN
 #define TESS_T_DONE_MIN 8  // finished cells waiting before the results phase runs
 #endif
 
 #ifndef TESS_T_PWARPS
 #define TESS_T_PWARPS 8    // producer warps per CTA (each serves 128 / PW consumer lanes)
+#endif
+#ifndef TESS_T_PASSES
+#define TESS_T_PASSES 4    // 32-particle passes per producer step
 #endif
 #ifndef TESS_T_TRIES
 #define TESS_T_TRIES 2     // candidates a lane may take (and reject) per round
@@ -91,6 +101,16 @@ struct __align__(16) ThreadShared {
     uint32_t cell[32 * ThreadCfg::WARPS];           // consumer -> producer: sorted slot of the cell under construction / C_IDLE / C_EXIT
 };
 static_assert(sizeof(ThreadShared) <= 232448, "tables and rings must fit the 227 KB of one SM");
+#ifdef TESS_T_STATS  // development build: phase / participation statistics of the state machines (printed after the launch)
+__device__ unsigned long long g_tstats[32];
+#define TCLK() clock64()
+#define TSTAT(i, v) atomicAdd(&g_tstats[i], (unsigned long long)(v))
+#define TSTAT_LEADER(i, v) do { if (lane == 0) atomicAdd(&g_tstats[i], (unsigned long long)(v)); } while (0)
+#else
+#define TSTAT(i, v) ((void)0)
+#define TCLK() 0ll
+#define TSTAT_LEADER(i, v) ((void)0)
+#endif
 constexpr uint32_t Q_END = 0xFFFFFFFFu, Q_END_EXH = 0xFFFFFFFEu, Q_HALO = 0x80000000u;
 constexpr uint32_t C_EXIT = 0xFFFFFFFFu, C_IDLE = 0xFFFFFFFEu;
 
@@ -405,12 +425,14 @@ __device__ void producer_warp(const ClipParams& P, ThreadShared* S, const int pw
         }
         if (__all_sync(TFULL, gone)) break;
         uint32_t need = __ballot_sync(TFULL, want);
+        TSTAT_LEADER(17, 1); TSTAT_LEADER(18, need ? 1 : 0);
         if (!need) {
-            __nanosleep(40);
+            __nanosleep(100);
             continue;
         }
         // ---- one step of the walk for each of them -----------------------------------------------------
         while (need) {
+            const long long t_step0 = TCLK();
             const int j = __ffs((int)need) - 1;
             need &= need - 1u;
             const int cj = pw * ThreadCfg::LPP + j;
@@ -443,86 +465,96 @@ __device__ void producer_warp(const ClipParams& P, ThreadShared* S, const int pw
                 }
                 if (lane == 0) cur = (end - cur > off0) ? cur + off0 : end;  // the part of the first entry's run already handed over
             }
-            // at most 32 particles of a run per step: the step ends with the first longer run
-            const bool longrun = end - cur > 32u;
-            if (longrun) end = cur + 32u;
-            const uint32_t longmask = __ballot_sync(TFULL, longrun);
-            const int l_lane = longmask ? __ffs((int)longmask) - 1 : 32;  // (< s_lane: lanes from s_lane on have empty runs)
-            if (lane > l_lane) {
-                end = cur;
-                halo = false;
-            }
-            // interface.rs:280-312 for the particles of the run: self, group, then (security mode) |r|^2 against the threshold
-            uint32_t pass = 0;
-            for (uint32_t k = 0; cur + k < end; ++k) {
-                const uint32_t slot = cur + k;
-                if (slot == self) continue;       // interface.rs:283/301 (by index)
-                if (P.target_group != -1)         // interface.rs:284/293 (-2: no particle carries the requested group)
-                    if (!(P.target_group >= 0 && P.groups_sorted[slot] == (uint64_t)P.target_group)) continue;
-                if (!radius_mode) {
-                    const double2* cq = reinterpret_cast<const double2*>(P.sorted + slot);
-                    const double2 a = __ldg(cq);
-                    const double zz = __ldg(reinterpret_cast<const double*>(cq + 1));
-                    const double rx = subd(a.x, qx), ry = subd(a.y, qy), rz = subd(zz, qz);  // interface.rs:322-326
-                    if (dot3(rx, ry, rz, rx, ry, rz) >= thr) continue;  // cannot have a vertex Outside (header of clip.cu)
-                }
-                pass |= 1u << k;
-            }
-            // items of this step in table order: per entry, its halo marker or its surviving particles; then the end marker
-            const bool ends = l_lane == 32 && s_lane < 32;  // the walk ends inside this step
-            uint32_t cnt = (uint32_t)__popc(pass) + (halo ? 1u : 0u);
-            if (ends && lane == s_lane) cnt = 1u;
-            uint32_t pre = cnt;  // inclusive scan
+            // The items of this step in table order: per entry its halo marker or the particles of its run, then (if the walk
+            // ends inside the step) the end marker.  Flattened: item p belongs to the entry whose prefix covers p, so the
+            // 32 lanes load 32 particles at a time whatever the lengths of the runs.
+            const bool ends = s_lane < 32;
+            uint32_t n = halo ? 1u : end - cur;
+            if (ends && lane == s_lane) n = 1u;
+            uint32_t inc = n;  // inclusive scan
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(TFULL, pre, d);
-                if (lane >= d) pre += o;
+                const uint32_t o = __shfl_up_sync(TFULL, inc, d);
+                if (lane >= d) inc += o;
             }
-            const uint32_t total = __shfl_sync(TFULL, pre, 31);
-            pre -= cnt;
-            const uint32_t emit = pre >= room0 ? 0u : (cnt < room0 - pre ? cnt : room0 - pre);
-            {
-                uint32_t m = pass;
-                for (uint32_t r = 0; r < emit; ++r) {
-                    uint32_t item;
-                    if (ends && lane == s_lane) item = (in_table || P.table_full || radius_mode) ? Q_END : Q_END_EXH;
-                    else if (halo) item = Q_HALO | e_idx;
-                    else {
-                        item = cur + (uint32_t)__ffs((int)m) - 1u;
-                        m &= m - 1u;
+            const uint32_t total = __shfl_sync(TFULL, inc, 31);
+            const uint32_t exc = inc - n;
+            const uint32_t lt = (1u << lane) - 1u;
+            uint32_t emitted = 0, p0 = 0, p_next = 0;
+            bool full = false;
+#pragma unroll 1
+            for (int pass_no = 0; pass_no < TESS_T_PASSES && p0 < total && !full; ++pass_no) {
+                const uint32_t p = p0 + (uint32_t)lane;
+                // entry of item p: the number of entries whose inclusive prefix is <= p
+                int en = 0;
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const uint32_t v = __shfl_sync(TFULL, inc, en + st - 1);
+                    if (v <= p) en += st;
+                }
+                const uint32_t e_exc = __shfl_sync(TFULL, exc, en), e_cur = __shfl_sync(TFULL, cur, en);
+                const bool e_halo = __shfl_sync(TFULL, halo ? 1 : 0, en) != 0;
+                const bool is_end = ends && en == s_lane;
+                uint32_t item = e_cur + (p - e_exc);
+                bool ok = p < total;
+                if (ok) {
+                    if (is_end) {
+                        item = (ti0 + (uint32_t)s_lane < P.table_len || P.table_full || radius_mode) ? Q_END : Q_END_EXH;
+                    } else if (e_halo) {
+                        item = Q_HALO | (ti0 + (uint32_t)en);
+                    } else {
+                        // interface.rs:280-312: self, group, then (security mode) |r|^2 against the threshold
+                        if (item == self) ok = false;  // interface.rs:283/301 (by index)
+                        if (ok && P.target_group != -1)    // interface.rs:284/293 (-2: no particle carries the requested group)
+                            if (!(P.target_group >= 0 && P.groups_sorted[item] == (uint64_t)P.target_group)) ok = false;
+                        if (ok && !radius_mode) {
+                            const double2* cq = reinterpret_cast<const double2*>(P.sorted + item);
+                            const double2 a = __ldg(cq);
+                            const double zz = __ldg(reinterpret_cast<const double*>(cq + 1));
+                            const double rx = subd(a.x, qx), ry = subd(a.y, qy), rz = subd(zz, qz);  // interface.rs:322-326
+                            if (dot3(rx, ry, rz, rx, ry, rz) >= thr) ok = false;  // cannot have a vertex Outside (header of clip.cu)
+                        }
                     }
-                    S->q[(tail0 + pre + r) % (uint32_t)ThreadCfg::QD][cj] = item;
+                }
+                const uint32_t m = __ballot_sync(TFULL, ok);
+                const uint32_t rank = emitted + (uint32_t)__popc(m & lt);
+                if (ok && rank < room0) S->q[(tail0 + rank) % (uint32_t)ThreadCfg::QD][cj] = item;
+                const uint32_t cnt = (uint32_t)__popc(m);
+                if (emitted + cnt > room0) {
+                    // the ring is full: the walk resumes after the last item that went in
+                    uint32_t mm = m;
+                    for (uint32_t r = emitted + 1u; r < room0; ++r) mm &= mm - 1u;
+                    p_next = p0 + (uint32_t)__ffs((int)mm);
+                    emitted = room0;
+                    full = true;
+                } else {
+                    emitted += cnt;
+                    p0 += 32u;
+                    p_next = p0 < total ? p0 : total;
+                    full = emitted == room0;
                 }
             }
-            // where the next step starts: the first entry that could not hand over everything, else the first long run,
-            // else after the 32 entries (or nowhere: the end marker is out)
-            const uint32_t partmask = __ballot_sync(TFULL, emit < cnt);
+            // where the next step starts
             uint32_t n_ti, n_off;
             bool n_done = false;
-            if (partmask) {
-                const int i = __ffs((int)partmask) - 1;
-                // particles of entry i's run up to and including the last one handed over
-                uint32_t used = 0;
-                if (lane == i && emit > 0u && !halo && !(ends && lane == s_lane)) {
-                    uint32_t m = pass;
-                    for (uint32_t r = 1; r < emit; ++r) m &= m - 1u;
-                    used = (uint32_t)__ffs((int)m);  // position of the emit-th survivor + 1
-                }
-                used = __shfl_sync(TFULL, used, i);
-                n_ti = ti0 + (uint32_t)i;
-                n_off = (i == 0 ? off0 : 0u) + used;
-            } else if (l_lane < 32 && l_lane < s_lane) {
-                n_ti = ti0 + (uint32_t)l_lane;
-                n_off = (l_lane == 0 ? off0 : 0u) + 32u;
-            } else if (ends) {
-                n_ti = ti0;
+            if (p_next >= total) {
+                n_ti = ti0 + (ends ? (uint32_t)s_lane : 32u);
                 n_off = 0;
-                n_done = true;
+                n_done = ends;  // the end marker was the last item
             } else {
-                n_ti = ti0 + 32u;
-                n_off = 0;
+                int en = 0;
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const uint32_t v = __shfl_sync(TFULL, inc, en + st - 1);
+                    if (v <= p_next) en += st;
+                }
+                const uint32_t e_exc = __shfl_sync(TFULL, exc, en);
+                n_ti = ti0 + (uint32_t)en;
+                n_off = (en == 0 ? off0 : 0u) + (p_next - e_exc);
             }
-            const uint32_t n_tail = tail0 + (total < room0 ? total : room0);
+            const uint32_t n_tail = tail0 + emitted;
+            TSTAT_LEADER(19, TCLK() - t_step0);
+            TSTAT_LEADER(13, 1); TSTAT_LEADER(14, emitted); TSTAT_LEADER(15, total); TSTAT_LEADER(16, room0);
             __syncwarp();
             if (lane == j) {
                 ti = n_ti; off = n_off; walk_done = n_done; tail = n_tail;
@@ -586,8 +618,10 @@ __global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1
     unsigned long long in = 0, out = 0;
     uint32_t c_nv = 0;
 
+    int idle = 0;
+    const long long t_k0 = TCLK();
     for (;;) {
-        bool progressed = false;
+        TSTAT_LEADER(0, 1);
         // ---- claim the next cells (one atomic per warp) and set up their start polyhedra -------------
         const uint32_t need = __ballot_sync(TFULL, state == S_NEW);
         if (need) {
@@ -616,126 +650,61 @@ __global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1
                     st_volatile_f64(&S->thr[c], stop_thr);
                     st_release(&S->cell[c], self_slot);  // the producer starts this cell's walk
                     state = S_FETCH;
-                    progressed = true;
                 }
             }
         }
-        if (__all_sync(TFULL, state == S_EXIT)) break;
+        if (__all_sync(TFULL, state == S_EXIT)) {
+            TSTAT_LEADER(24, TCLK() - t_k0);
+            break;
+        }
 
-        // ---- cut: when enough lanes wait for it, or nobody can do anything else --------------------------
-        {
-            const uint32_t m_cut = __ballot_sync(TFULL, state == S_CUT);
-            const uint32_t m_can = __ballot_sync(TFULL, state == S_FETCH && (staged || ld_acquire(&S->tail[c]) != head));
-            if (m_cut && (__popc(m_cut) >= TESS_T_CUT_MIN || m_can == 0u)) {
-                if (state == S_CUT) {
-                    progressed = true;
-                    const int rc = thread_cut(M, pl, cand_slot, in, out, c_nv);
-                    if (rc != TCUT_OK) {
-                        status |= ST_TABLE_EXHAUSTED;  // handed back: redone by the warp-per-cell kernel
-                        failed = true;
-                        st_volatile_f64(&S->thr[c], -2.0);  // every key exceeds it: the producer sends the end marker
-                    } else if (!radius_mode && ((out >> far_v) & 1ull)) {
-                        // the farthest vertex only ever moves inwards: new vertices lie between an Outside and an Inside
-                        // one, so max|v|^2 changes only when the vertex that attained it was cut off
-                        stop_thr = mul(4.0, M.max_radius_sq(far_v));
-                        st_volatile_f64(&S->thr[c], stop_thr);
-                    }
-                    state = S_FETCH;
+        // ---- stage the next ring item; a particle's position is requested now and used a phase later ---------
+        if (!staged && (state == S_FETCH || state == S_CUT)) {
+            if (ld_acquire(&S->tail[c]) != head) {
+                st_item = S->q[head % (uint32_t)ThreadCfg::QD][c];
+                ++head;
+                st_release(&S->head[c], head);
+                staged = true;
+                if (st_item < Q_HALO) {
+                    const double2* cq = reinterpret_cast<const double2*>(P.sorted + st_item);
+                    const double2 a = __ldg(cq);
+                    sx = a.x; sy = a.y;
+                    sz = __ldg(reinterpret_cast<const double*>(cq + 1));
                 }
             }
         }
 
-        // ---- results: weighted normals, areas, volume, neighbours ------------------------------------
-        {
-            const uint32_t m_done = __ballot_sync(TFULL, state == S_DONE);
-            const uint32_t m_busy = __ballot_sync(TFULL, state == S_CUT || (state == S_FETCH && (staged || ld_acquire(&S->tail[c]) != head)));
-            if (m_done && (__popc(m_done) >= TESS_T_DONE_MIN || m_busy == 0u)) {
-                if (state == S_DONE) {
-                    progressed = true;
-                    const long long self_id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + self_slot) + 3));
-                    const size_t row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
-                    const size_t srow = P.stage_by_work ? (size_t)work : row;
-                    uint32_t nf = 0;
-                    double vol = 0.0;
-                    if (!failed) {
-                        nf = (uint32_t)__popc(M.flive);
-                        uint32_t rank = 0;
-                        for (uint32_t fm = M.flive; fm; fm &= fm - 1u) {
-                            const uint32_t f = (uint32_t)__ffs((int)fm) - 1u;
-                            // Polyhedron::weighted_normal (polyhedron.rs:776-808)
-                            const uint32_t s = M.t->fstart[f][lane];
-                            uint32_t w = M.ew(s);
-                            const uint32_t av = ew_tgt(w);
-                            const Vec3 A = {M.x(av), M.y(av), M.z(av)};
-                            uint32_t e = ew_next(w);
-                            w = M.ew(e);
-                            uint32_t tv = ew_tgt(w);
-                            Vec3 cu = sub(Vec3{M.x(tv), M.y(tv), M.z(tv)}, A);
-                            e = ew_next(w);
-                            Vec3 wn = {0.0, 0.0, 0.0};
-                            int guard = 0;
-                            while (e != s && guard++ < ThreadCfg::E) {
-                                w = M.ew(e);
-                                tv = ew_tgt(w);
-                                const Vec3 prev = cu;
-                                cu = sub(Vec3{M.x(tv), M.y(tv), M.z(tv)}, A);
-                                wn = add(wn, cross(prev, cu));
-                                e = ew_next(w);
-                            }
-                            // volume = volume + dot(...) face after face in ascending slot order (polyhedron.rs:843-850)
-                            vol = addd(vol, dot(A, wn));
-                            if (rank < P.fstride) {
-                                const uint32_t nb = M.t->fnbr[f][lane];
-                                long long id;
-                                if (nb >= WALL0) id = -(long long)(nb - WALL0 + 1u);  // container faces: -1..-6
-                                else id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + nb) + 3));
-                                P.st_nbr[srow * P.fstride + rank] = id;
-                                if (P.st_area) P.st_area[srow * P.fstride + rank] = mul(0.5, __dsqrt_rn(dot(wn, wn)));  // interface.rs:408-410
-                            }
-                            ++rank;
-                        }
-                        if (nf > P.fstride) {  // cannot happen with F <= fstride; kept for a caller with a smaller staging stride
-                            status |= ST_TABLE_EXHAUSTED;
-                            failed = true;
-                        }
-                    }
-                    if (failed && P.failed_slots) {
-                        const uint32_t k = atomicAdd(P.n_failed, 1u);
-                        if (k < P.failed_cap) P.failed_slots[k] = self_slot;
-                        atomicAdd(P.n_failed + 4, 1u);  // "only ran out of table": the next tier is the warp-per-cell kernel, not the medium one
-                    }
-                    P.vol[row] = failed ? 0.0 : __ddiv_rn(vol, 6.0);  // polyhedron.rs:854
-                    P.nfaces[row] = failed ? 0u : nf;
-                    P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
-                    if (P.cell_id) P.cell_id[row] = self_id;
-                    state = S_NEW;
-                }
+        // ---- which phases run: a phase costs the same whatever the number of lanes in it, so each waits for enough
+        //      lanes — unless nothing else can happen
+        const uint32_t m_test = __ballot_sync(TFULL, state == S_FETCH && staged);
+        const uint32_t m_cut = __ballot_sync(TFULL, state == S_CUT);
+        const uint32_t m_done = __ballot_sync(TFULL, state == S_DONE);
+        const uint32_t m_starved = __ballot_sync(TFULL, state == S_FETCH && !staged);
+        const int n_test = __popc(m_test), n_cut = __popc(m_cut), n_done = __popc(m_done);
+        bool run_test = n_test >= TESS_T_TEST_MIN, run_cut = n_cut >= TESS_T_CUT_MIN, run_done = n_done >= TESS_T_DONE_MIN;
+        if (!run_test && !run_cut && !run_done) {
+            if ((n_test | n_cut | n_done) == 0 || (m_starved && idle < TESS_T_SPINS)) {
+                ++idle;
+                TSTAT_LEADER(7, 1);
+                __nanosleep(20);
+                continue;
             }
+            // the largest group goes (a results phase is the longest: it goes last)
+            if (n_test >= n_cut && n_test > 0) run_test = true;
+            else if (n_cut > 0) run_cut = true;
+            else run_done = true;
         }
+        idle = 0;
 
-        // ---- take candidates from the ring (interface.rs:280-312 in the producer's order) ------------------
-#pragma unroll 1
-        for (int tries = 0; tries <= TESS_T_TRIES; ++tries) {
-            // stage the next item; a particle's position is requested now and used a phase later
-            if (!staged && state != S_EXIT && state != S_NEW && state != S_DONE) {
-                if (ld_acquire(&S->tail[c]) != head) {
-                    st_item = S->q[head % (uint32_t)ThreadCfg::QD][c];
-                    ++head;
-                    st_release(&S->head[c], head);
-                    staged = true;
-                    progressed = true;
-                    if (st_item < Q_HALO) {
-                        const double2* cq = reinterpret_cast<const double2*>(P.sorted + st_item);
-                        const double2 a = __ldg(cq);
-                        sx = a.x; sy = a.y;
-                        sz = __ldg(reinterpret_cast<const double*>(cq + 1));
-                    }
-                }
-            }
-            if (tries == TESS_T_TRIES) break;
+        // ---- take the staged candidates (interface.rs:280-312 in the producer's order) and classify every live vertex
+        //      against each one's bisector plane (find_outgoing_edge's vertex scan, polyhedron.rs:399-405, and every later
+        //      vector_location call of the walk)
+        const long long t_ph0 = TCLK();
+        if (run_test) {
+            TSTAT_LEADER(3, 1); TSTAT_LEADER(4, n_test);
             if (state == S_FETCH && staged) {
                 staged = false;
-                progressed = true;
+                TSTAT(11, 1);
                 if (st_item >= Q_END_EXH) {
                     // the end of the walk; a table that ended before a key exceeded the threshold has to be widened
                     // (keys ascend: no key exceeded it iff the last one does not)
@@ -758,11 +727,7 @@ __global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1
                     }
                 }
             }
-        }
-
-        // ---- classify every live vertex against the candidate's bisector plane (find_outgoing_edge's vertex scan,
-        //      polyhedron.rs:399-405, and every later vector_location call of the walk) ------------------
-        if (state == S_TEST) {
+            if (state == S_TEST) {
             {
                 // Plane::halfway_from_origin_to (vector3.rs:223-225); mag_sq(rel) is r2
                 const double m = __dsqrt_rn(r2);
@@ -798,8 +763,96 @@ __global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1
             } else {
                 state = S_CUT;
             }
+            }
         }
-        if (!__any_sync(TFULL, progressed)) __nanosleep(20);
+
+        const long long t_ph1 = TCLK();
+        TSTAT_LEADER(21, t_ph1 - t_ph0);
+        // ---- cut ---------------------------------------------------------------------------------------
+        if (run_cut) {
+            TSTAT_LEADER(1, 1); TSTAT_LEADER(2, n_cut);
+            if (state == S_CUT) {
+                const int rc = thread_cut(M, pl, cand_slot, in, out, c_nv);
+                if (rc != TCUT_OK) {
+                    status |= ST_TABLE_EXHAUSTED;  // handed back: redone by the warp-per-cell kernel
+                    failed = true;
+                    st_volatile_f64(&S->thr[c], -2.0);  // every key exceeds it: the producer sends the end marker
+                } else if (!radius_mode && ((out >> far_v) & 1ull)) {
+                    // the farthest vertex only ever moves inwards: new vertices lie between an Outside and an Inside
+                    // one, so max|v|^2 changes only when the vertex that attained it was cut off
+                    stop_thr = mul(4.0, M.max_radius_sq(far_v));
+                    st_volatile_f64(&S->thr[c], stop_thr);
+                }
+                state = S_FETCH;
+            }
+        }
+
+        const long long t_ph2 = TCLK();
+        TSTAT_LEADER(22, t_ph2 - t_ph1);
+        // ---- results: weighted normals, areas, volume, neighbours ------------------------------------
+        if (run_done) {
+            TSTAT_LEADER(5, 1); TSTAT_LEADER(6, n_done);
+            if (state == S_DONE) {
+                const long long self_id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + self_slot) + 3));
+                const size_t row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
+                const size_t srow = P.stage_by_work ? (size_t)work : row;
+                uint32_t nf = 0;
+                double vol = 0.0;
+                if (!failed) {
+                    nf = (uint32_t)__popc(M.flive);
+                    uint32_t rank = 0;
+                    for (uint32_t fm = M.flive; fm; fm &= fm - 1u) {
+                        const uint32_t f = (uint32_t)__ffs((int)fm) - 1u;
+                        // Polyhedron::weighted_normal (polyhedron.rs:776-808)
+                        const uint32_t s = M.t->fstart[f][lane];
+                        uint32_t w = M.ew(s);
+                        const uint32_t av = ew_tgt(w);
+                        const Vec3 A = {M.x(av), M.y(av), M.z(av)};
+                        uint32_t e = ew_next(w);
+                        w = M.ew(e);
+                        uint32_t tv = ew_tgt(w);
+                        Vec3 cu = sub(Vec3{M.x(tv), M.y(tv), M.z(tv)}, A);
+                        e = ew_next(w);
+                        Vec3 wn = {0.0, 0.0, 0.0};
+                        int guard = 0;
+                        while (e != s && guard++ < ThreadCfg::E) {
+                            w = M.ew(e);
+                            tv = ew_tgt(w);
+                            const Vec3 prev = cu;
+                            cu = sub(Vec3{M.x(tv), M.y(tv), M.z(tv)}, A);
+                            wn = add(wn, cross(prev, cu));
+                            e = ew_next(w);
+                        }
+                        // volume = volume + dot(...) face after face in ascending slot order (polyhedron.rs:843-850)
+                        vol = addd(vol, dot(A, wn));
+                        if (rank < P.fstride) {
+                            const uint32_t nb = M.t->fnbr[f][lane];
+                            long long id;
+                            if (nb >= WALL0) id = -(long long)(nb - WALL0 + 1u);  // container faces: -1..-6
+                            else id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + nb) + 3));
+                            P.st_nbr[srow * P.fstride + rank] = id;
+                            if (P.st_area) P.st_area[srow * P.fstride + rank] = mul(0.5, __dsqrt_rn(dot(wn, wn)));  // interface.rs:408-410
+                        }
+                        ++rank;
+                    }
+                    if (nf > P.fstride) {  // cannot happen with F <= fstride; kept for a caller with a smaller staging stride
+                        status |= ST_TABLE_EXHAUSTED;
+                        failed = true;
+                    }
+                }
+                if (failed && P.failed_slots) {
+                    const uint32_t k = atomicAdd(P.n_failed, 1u);
+                    if (k < P.failed_cap) P.failed_slots[k] = self_slot;
+                    atomicAdd(P.n_failed + 4, 1u);  // "only ran out of table": the next tier is the warp-per-cell kernel, not the medium one
+                }
+                P.vol[row] = failed ? 0.0 : __ddiv_rn(vol, 6.0);  // polyhedron.rs:854
+                P.nfaces[row] = failed ? 0u : nf;
+                P.status[row] = status | (P.mark_large ? ST_LARGE_PATH : 0u);
+                if (P.cell_id) P.cell_id[row] = self_id;
+                state = S_NEW;
+            }
+        }
+        TSTAT_LEADER(23, TCLK() - t_ph2);
     }
 }
 
@@ -820,9 +873,31 @@ void launch_thread_cfg(const ClipParams& p, cudaStream_t s) {
     const unsigned int want = (unsigned int)((p.n_work + ThreadCfg::WARPS * 32 - 1) / (ThreadCfg::WARPS * 32));
     const unsigned int grid = std::min<unsigned int>(want, (unsigned int)sms);
     TESS_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), s));
+#ifdef TESS_T_STATS
+    {
+        unsigned long long z[32] = {0};
+        TESS_CUDA_CHECK(cudaMemcpyToSymbol(g_tstats, z, sizeof(z)));
+    }
+#endif
     clip_thread_kernel<<<grid, threads, smem, s>>>(p);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
+#ifdef TESS_T_STATS
+    {
+        unsigned long long h[32];
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        TESS_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_tstats, sizeof(h)));
+        const double nc = (double)p.n_work;
+        std::fprintf(stderr, "[thread stats] cells %u | per consumer warp-cell-batch(32 cells): rounds %.1f cut phases %.1f (lanes %.1f) test phases %.1f (lanes %.1f) done phases %.1f (lanes %.1f)\n",
+                     p.n_work, h[0] / nc * 32, h[1] / nc * 32, h[2] / (double)(h[1] ? h[1] : 1), h[3] / nc * 32, h[4] / (double)(h[3] ? h[3] : 1), h[5] / nc * 32, h[6] / (double)(h[5] ? h[5] : 1));
+        std::fprintf(stderr, "[thread stats] lane-rounds per round: starved %.2f waiting-cut %.2f waiting-done %.2f exited %.2f | items consumed per cell %.1f\n",
+                     h[7] / (double)h[0], h[8] / (double)h[0], h[9] / (double)h[0], h[10] / (double)h[0], h[11] / nc);
+        std::fprintf(stderr, "[thread stats] consumer warp cycles per 32 cells: total %.0f test %.0f cut %.0f results %.0f | per phase: test %.0f cut %.0f results %.0f | producer cycles per step %.0f\n",
+                     h[24] / nc * 32, h[21] / nc * 32, h[22] / nc * 32, h[23] / nc * 32, h[21] / (double)(h[3] ? h[3] : 1), h[22] / (double)(h[1] ? h[1] : 1), h[23] / (double)(h[5] ? h[5] : 1), h[19] / (double)(h[13] ? h[13] : 1));
+        std::fprintf(stderr, "[thread stats] producer: steps per cell %.2f items/step %.2f particles+markers/step %.1f room/step %.2f | polls %.3g with work %.3g\n",
+                     h[13] / nc, h[14] / (double)(h[13] ? h[13] : 1), h[15] / (double)(h[13] ? h[13] : 1), h[16] / (double)(h[13] ? h[13] : 1), (double)h[17], (double)h[18]);
+    }
+#endif
 #endif
 }
 
