@@ -125,14 +125,22 @@ def load_peaks() -> dict:
 
 
 def ncu_traffic_per_launch():
-    """dram bytes per clip-kernel launch from the committed ncu capture of this workload, if any."""
+    """DRAM bytes and warp instructions per clip-kernel launch from the committed ncu capture (profiles/clip_kernel_traffic.json,
+    written by profiles/make_traffic_json.py).  The file carries a hash of the kernel sources: a capture of other code is refused."""
     p = os.path.join(ROOT, "profiles", "clip_kernel_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        from make_traffic_json import kernel_sources_sha256
+
+        if d.get("kernel_sources_sha256") != kernel_sources_sha256():
+            log("note: profiles/clip_kernel_traffic.json was captured from other kernel sources (hash differs): not used")
             return None
-    return None
+        return d
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,7 +196,7 @@ def run_reference_arm(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": "voronoi_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * per_cell * sample, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n, kind, seed, 0),
+        "config": workload_config(args, n, kind, seed, args.gpus),  # the job the GPU arm runs at this N; this arm does it on the host cores
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": desc,
                          "note": "C++ restatement of the reference (oracle/): the Rust crate cannot be built here and its clipper is unfinished"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +207,9 @@ def run_reference_arm(args, rank: int, world: int):
 def workload_config(args, n, kind, seed, world):
     return {
         "workload": f"BASELINE config: {n} {kind} points (seed {seed}) in the unit cube, non-periodic box, outputs volume+face areas+neighbours",
-        "n_points": n, "container": BOX, "parallelism": f"x-slabs over {max(world, 1)} GPU(s), halo 4 grid planes" if world > 1 else "single GPU",
+        "n_points": n, "container": BOX,
+        "parallelism": (f"x-slabs over {world} GPUs, halo 4 grid planes; every step re-packs and re-exchanges the particles (one all-to-all of 32-byte records), "
+                        "the slab plan (bounds, cuts, exchange counts) is reused while the particle set is unchanged") if world > 1 else "single GPU",
         "l2": "inputs (240 MB of positions at 10M points) exceed the 126 MB L2; no explicit flush between steps",
     }
 
@@ -279,8 +289,9 @@ def main():
             diagram.initialize(T.Polyhedron(*BOX), stream=stream)
             state["batch"] = diagram.compute_all_cells(stream=stream, **opts)
         else:
-            res = D.compute_sharded(backend, xyz_dev, start, n, BOX, dist=dist, halo=4, opts=opts)
-            state["batch"], state["res"] = res.batch, res
+            res = D.compute_sharded(backend, xyz_dev, start, n, BOX, dist=dist, halo=4, opts=opts, plan=state.get("plan"))
+            state["batch"], state["res"], state["plan"] = res.batch, res, res.plan
+            assert res.halo_ok
         return state["batch"]
 
     def barrier():
@@ -358,8 +369,9 @@ def main():
                 bb = diagram.compute_all_cells_to_host(h_vol, h_off, h_nbr, h_area, h_stat, n_chunks=args.e2e_chunks, stream=stream, **opts)
             else:
                 stage.copy_(host_in, non_blocking=True)  # pinned host -> device
-                res = D.compute_sharded(backend, stage, start, n, BOX, dist=dist, halo=4,
+                res = D.compute_sharded(backend, stage, start, n, BOX, dist=dist, halo=4, plan=state.get("plan"),
                                         opts=dict(opts, host_sink=(h_vol, h_off, h_nbr, h_area, h_stat, args.e2e_chunks)))
+                state["plan"] = res.plan
                 bb = res.batch
             assert bb.n_faces <= cap_faces and bb.n_cells <= n_cells_local + 1024
             torch.cuda.current_stream(dev).synchronize()
@@ -394,11 +406,12 @@ def main():
     alg_bytes = bytes_per_cell * n_cells_local
     achieved = alg_bytes / (clip_avg * 1e-3) / 1e9
     traffic = ncu_traffic_per_launch()
-    roofline = {
-        "kernel": "clip_kernel<SmallCfg>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+    kname = "clip_kernel<SmallCfg, no counters, no serial walk> (main pass)"
+    roofline_hbm = {
+        "kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peaks["source"], "avg_launch_ms": clip_avg,
         "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": clip_avg / ms_per_step,
-        "note": "the clip kernel is bound by instruction issue, not by HBM (DESIGN.md); the HBM fraction is reported because the roofline schema asks for it, the binding limit is in roofline_issue",
+        "note": "not the binding roof: the clip kernel is bound by instruction issue (roofline), the HBM line explains why traffic does not matter",
     }
     fp64_peak = T._lib.C.c_double(0)
     T._lib.check(lib.tess_measure_fp64_peak(local_rank, T._lib.C.byref(fp64_peak)))
@@ -411,8 +424,9 @@ def main():
     flops = 8 * c["visited"] + 13 * c["tested"] + 6 * c["vertex_classifications"] + 27 * c["new_vertices"] + c["faces"] * (15 * mean_face_verts - 14)
     fp64_ach = flops / (clip_avg * 1e-3) / 1e12
     roofline_fp64 = {
-        "kernel": "clip_kernel<SmallCfg>", "bound": "fp64", "achieved": fp64_ach, "peak": float(fp64_peak.value), "unit": "TFLOP/s", "frac": fp64_ach / max(1e-9, float(fp64_peak.value)),
+        "kernel": kname, "bound": "fp64", "achieved": fp64_ach, "peak": float(fp64_peak.value), "unit": "TFLOP/s", "frac": fp64_ach / max(1e-9, float(fp64_peak.value)),
         "peak_source": "measured in this run: register-resident DFMA loop (tess_measure_fp64_peak)", "flops_per_cell": flops / nc,
+        "traffic": (traffic or {}).get("dram_bytes_per_launch"), "avg_launch_ms": clip_avg, "share_of_step": clip_avg / ms_per_step,
         "counters_per_cell": {k: v / nc for k, v in c.items()},
     }
     # the roof that binds: warp-instruction issue slots (4 schedulers per SM, one instruction per cycle each).
@@ -420,14 +434,18 @@ def main():
     roofline_issue = None
     if traffic and traffic.get("warp_instructions_per_launch") and clocks and clocks.get("sm_mhz"):
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        inst_per_cell = traffic["warp_instructions_per_launch"] / 1.0e7  # the capture's launch held 10^7 cells
+        inst_per_cell = traffic["warp_instructions_per_launch"] / float(traffic.get("cells_per_launch", 1.0e7))
         ach = inst_per_cell * n_cells_local / (clip_avg * 1e-3) / 1e12
         peak = sms * 4 * clocks["sm_mhz"] * 1e6 / 1e12
-        roofline_issue = {"kernel": "clip_kernel<SmallCfg>", "bound": "issue", "achieved": ach, "peak": peak, "unit": "T warp-instr/s", "frac": ach / peak,
+        roofline_issue = {"kernel": kname, "bound": "issue", "achieved": ach, "peak": peak, "unit": "T warp-instr/s", "frac": ach / peak,
                           "warp_instructions_per_cell": inst_per_cell,
                           "peak_source": "%d SMs x 4 schedulers x %.0f MHz (median SM clock under load)" % (sms, clocks["sm_mhz"]),
-                          "note": "instruction count from profiles/clip_kernel_traffic.json (ncu, uniform 10M capture); ncu's own smsp__issue_active for that capture is %.1f %%" % traffic.get("issue_active_pct", float("nan")),
-                          "capture_note": traffic.get("capture_is_one_change_behind")}
+                          "traffic": traffic.get("dram_bytes_per_launch"), "avg_launch_ms": clip_avg, "share_of_step": clip_avg / ms_per_step,
+                          "note": "SURVEY 8(d): the clip kernel is bound by issue slots, not by HBM or the FP64 pipe.  achieved = warp instructions per cell (ncu capture of exactly these kernel sources, "
+                                  "profiles/clip_kernel_traffic.json: %s) x cells per launch / live CUDA-event launch time; ncu's own smsp__issue_active for that capture is %.1f %%"
+                                  % (traffic.get("source"), traffic.get("issue_active_pct", float("nan")))}
+    # `roofline` is the roof that binds (issue slots) when a capture of the shipped kernel sources is committed; else the FP64 pipe, SURVEY 8(d)'s other candidate
+    roofline = roofline_issue or dict(roofline_fp64, note="no ncu capture of these kernel sources is committed (profiles/clip_kernel_traffic.json): the issue-slot line cannot be computed; FP64 pipe instead")
     bin_avg = float(np.mean(bin_ms))
     n_binned = (state["res"].n_received if world > 1 else n_local)
     bin_ach = BYTES_PER_POINT_BINNING * n_binned / (bin_avg * 1e-3) / 1e9
@@ -454,7 +472,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, n, kind, seed, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / max(1, args.steps),
-        "roofline": roofline, "roofline_issue": roofline_issue, "roofline_fp64": roofline_fp64, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline,
         "checks": {"cells": int(ncell[0].item()), "faces": int(ncell[1].item()), "abs_volume_closure_error": closure, "wall_ms_per_step": wall_ms / args.steps,
                    "outputs_ms": float(np.mean(out_ms))},
     }

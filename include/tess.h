@@ -218,6 +218,16 @@ int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t i
 
 /* ---- Telemetry used by bench.py ----------------------------------------------------------- */
 
+/* The same routing with one 32-byte record {x, y, z, id (bit pattern of the i64)} per particle, so that ONE all-to-all
+ * carries positions and ids, and without a host round trip when the counts are known: planned_counts (host, n_ranks, or
+ * NULL) are the per-destination counts of an earlier call on the same particle set; the call then runs no counting pass
+ * and does not synchronise the stream.  counts_dev[n_ranks] (device) receives the counts actually packed — with a plan,
+ * compare them with it (a mismatch means the set changed and the packed records must be discarded);
+ * counts_host (host, nullable) receives the counts used for the layout.  Returns TESS_ERR_NOMEM if cap (records) is too small. */
+int tess_pack_records(const double* xyz_dev, const int64_t* ids_dev, int64_t id_base, size_t n, const double bounds[6], uint64_t n_global, int n_ranks, const uint32_t* plane_lo, const uint32_t* plane_hi, const uint64_t* planned_counts, uint64_t* counts_host, uint64_t* counts_dev, double* out_rec_dev, size_t cap, void* stream);
+/* Diagram::add_particle (interface.rs:44-56) for n device-resident 32-byte records of tess_pack_records (after the exchange). */
+int tess_diagram_add_records_device(tess_diagram* d, const double* rec_dev, size_t n, void* stream);
+
 /* CUDA-event durations (ms, on the launching stream) of the last computation:
  * ms[0] clip kernel (small-cell pass), ms[1] redo passes (wider table, medium and large configurations), ms[2] scans + CSR compaction, ms[3] whole call. */
 int tess_result_timings(const tess_result* r, double ms[4]);

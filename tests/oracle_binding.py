@@ -24,11 +24,29 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 
+def _host_tag() -> str:
+    """The oracle is built with -march=native (the CPU baseline at the host's best): a library built on another
+    machine (the prebuilt file travels with the repo) is rebuilt for the cores it runs on."""
+    import hashlib
+
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    return hashlib.sha256(flags.encode()).hexdigest()[:16]
+
+
 def build(force: bool = False) -> str:
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("tess_oracle.cpp", "tess_oracle_capi.cpp", "tess_oracle.hpp", "Makefile")]
-    stale = force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    tag_path = _LIB_PATH + ".host"
+    tag = _host_tag()
+    built_for = open(tag_path).read().strip() if os.path.exists(tag_path) else ""
+    stale = force or not os.path.exists(_LIB_PATH) or built_for != tag or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if stale:
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+        with open(tag_path, "w") as f:
+            f.write(tag)
     return _LIB_PATH
 
 

@@ -33,7 +33,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_global, seed, thin_halo, out):
+def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -72,7 +72,8 @@ def _worker(rank, world, port, n_global, seed, thin_halo, out):
 
         def compute(self, xyz, ids, box, b, n_global, own, local, opts):
             gx, _ = self._planes(xyz, b, n_global)
-            assert np.all((gx >= local[0]) & (gx < local[1])), "received a particle outside the local planes"
+            if not getattr(self, "planned", False):  # (records laid out by a stale plan are garbage: the step is discarded and redone)
+                assert np.all((gx >= local[0]) & (gx < local[1])), "received a particle outside the local planes"
             owned = (gx >= own[0]) & (gx < own[1])
             halo_lo, halo_hi = own[0] - local[0], local[1] - own[1]
             self.calls.append(dict(own=own, local=local, n=len(gx)))
@@ -83,27 +84,63 @@ def _worker(rank, world, port, n_global, seed, thin_halo, out):
             batch = dict(ids=ids.numpy()[owned], recv_ids=ids.numpy(), bounds=np.array(b), own=own, local=local)
             return batch, int(owned.sum()), flagged
 
+    class RecordBackend(NumpyBackend):
+        """The one-all-to-all path: 32-byte records, exchange counts known from a plan."""
+
+        has_records = True
+
+        def pack_records(self, xyz, id_base, b, n_global, lo, hi, planned_counts=None):
+            counts, px, pi = self.pack(xyz, id_base, b, n_global, lo, hi)
+            rec = torch.cat([px, pi.view(torch.float64).reshape(-1, 1)], dim=1)
+            self.planned = planned_counts is not None
+            if planned_counts is not None:  # the layout follows the plan: segments cut or padded to the planned counts
+                seg, o = [], 0
+                for have, want in zip(counts, planned_counts):
+                    part = rec[o:o + min(have, want)]
+                    seg.append(torch.cat([part, torch.zeros((want - part.shape[0], 4), dtype=torch.float64)]))
+                    o += have
+                rec = torch.cat(seg)
+            return (list(planned_counts) if planned_counts is not None else counts), rec, torch.tensor(counts, dtype=torch.int64)
+
+        def compute_records(self, rec, box, b, n_global, own, local, opts):
+            batch, n_owned, flagged = self.compute(rec[:, :3].contiguous(), rec[:, 3].contiguous().view(torch.int64), box, b, n_global, own, local, opts)
+            return batch, n_owned, torch.tensor([1 if flagged else 0], dtype=torch.int32)
+
     per = n_global // world
     start = rank * per
     n_local = per if rank < world - 1 else n_global - start
     # ranks hold arbitrary (index-contiguous, spatially random) subsets of one global stream
     xyz = torch.from_numpy(gen.uniform(n_local, seed, start=start))
-    be = NumpyBackend()
+    be = RecordBackend() if records else NumpyBackend()
     res = D.compute_sharded(be, xyz, start, n_global, [0, 0, 0, 1, 1, 1], dist=dist, halo=1 if thin_halo else 4)
+    if records:
+        # the same particles again, with the plan: no planning collectives, same exchange, same result
+        first = res
+        n_before = len(be.calls)
+        res = D.compute_sharded(be, xyz, start, n_global, [0, 0, 0, 1, 1, 1], dist=dist, plan=first.plan)
+        assert be.planned and len(be.calls) == n_before + 1 and res.rounds == 1 and res.halo == first.halo
+        assert np.array_equal(res.batch["recv_ids"], first.batch["recv_ids"]) and np.array_equal(res.batch["ids"], first.batch["ids"])
+        # other particles with the old plan (a broken promise): detected through the counts, planned again
+        xyz2 = torch.from_numpy(gen.uniform(n_local, seed + 1, start=start))
+        again = D.compute_sharded(be, xyz2, start, n_global, [0, 0, 0, 1, 1, 1], dist=dist, plan=first.plan)
+        fresh = D.compute_sharded(be, xyz2, start, n_global, [0, 0, 0, 1, 1, 1], dist=dist)
+        assert np.array_equal(again.batch["recv_ids"], fresh.batch["recv_ids"]) and again.plan.send_counts == fresh.plan.send_counts
+        assert res.halo_ok and again.halo_ok
     np.savez(out.format(rank=rank), ids=res.batch["ids"], recv_ids=res.batch["recv_ids"], bounds=res.batch["bounds"], own=np.array(res.own),
              local=np.array(res.local), halo=res.halo, rounds=res.rounds, n_owned=res.n_owned, n_calls=len(be.calls))
     dist.barrier()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("records", [False, True])
 @pytest.mark.parametrize("thin_halo", [False, True])
-def test_two_rank_slab_exchange(tmp_path, gen, thin_halo):
+def test_two_rank_slab_exchange(tmp_path, gen, thin_halo, records):
     import torch.multiprocessing as mp
 
     D = importlib.import_module("the-tessellator_b200.distributed")
     world, n, seed = 2, 20_000, 77
     out = str(tmp_path / "rank{rank}.npz")
-    mp.spawn(_worker, args=(world, _free_port(), n, seed, thin_halo, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, seed, thin_halo, out, records), nprocs=world, join=True)
     pts = gen.uniform(n, seed)
     cpd = D.cells_per_dimension(n)
     b = np.array([pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max(), pts[:, 2].min(), pts[:, 2].max()])
@@ -125,7 +162,9 @@ def test_two_rank_slab_exchange(tmp_path, gen, thin_halo):
         assert np.array_equal(np.sort(r[k]["recv_ids"]), expect)  # owned + ghost planes, nothing else
         h = int(r[k]["halo"])
         assert lo == max(0, r[k]["own"][0] - h) and hi == min(cpd, r[k]["own"][1] + h)
-    if thin_halo:  # halo 1 < 3 needed: widened 1 -> 2 -> 4, both ranks in lock-step
+    if thin_halo and records:  # the saved result is the planned second step: one round at the halo the first one found
+        assert all(int(r[k]["rounds"]) == 1 and int(r[k]["halo"]) == 4 for k in range(world))
+    elif thin_halo:  # halo 1 < 3 needed: widened 1 -> 2 -> 4, both ranks in lock-step
         assert all(int(r[k]["rounds"]) == 3 and int(r[k]["halo"]) == 4 for k in range(world))
     else:
         assert all(int(r[k]["rounds"]) == 1 and int(r[k]["halo"]) == 4 for k in range(world))

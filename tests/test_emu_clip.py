@@ -248,3 +248,76 @@ def test_small_configuration_without_the_serial_walk(eb, gen):
     e = g2.clip(large="fast", count=False)
     assert not (e.status & 0x2).any() or g2.table_full == 0
     _check(e, g2.oracle_cells(), "fast on random input", expect_all=False)
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "bcc", "cubic", "on_walls"])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_thread_per_cell_kernel(eb, gen, case, reverse):
+    """CLIP_THREAD (clip_thread.cu): consumer warps build one cell per thread, producer warps walk the search table and
+    feed them through per-lane rings in shared memory.  Every cell it finishes is the oracle's cell bit for bit; what its
+    tables cannot hold — and every cell that meets a vertex ON a plane (the exact lattice) — is handed back flagged like a
+    cell that ran out of search table, and the warp-per-cell kernel finishes those."""
+    base = gen.uniform(2500, 81)
+    pts = {
+        "uniform": lambda: gen.uniform(3000, 51),
+        "clustered": lambda: gen.clustered(4000, 4, k=4),  # long particle runs per grid cell: the producer's partial steps
+        "bcc": lambda: gen.bcc(9, 5),
+        "cubic": lambda: np.concatenate([gen.uniform(1500, 5), 0.25 + 0.5 * gen.simple_cubic(6)]),
+        "on_walls": lambda: np.concatenate([base, np.round(gen.uniform(300, 82), 0) * np.array([1, 1, 0]) + gen.uniform(300, 83) * np.array([0, 0, 1])]),
+    }[case]()
+    g = eb.EmuGrid(pts, BOX, table_radius=-1)
+    r = g.oracle_cells()
+    e = g.clip(large="thread", count=False, reverse=reverse)
+    handed_back = (e.status & 0x2) != 0
+    assert not (e.status & (0x4 | 0x10)).any()
+    ok = _check(e, r, "thread " + case, expect_all=False)
+    assert np.array_equal(ok, ~handed_back)
+    assert ok.mean() > {"uniform": 0.95, "clustered": 0.75, "bcc": 0.99, "cubic": 0.6, "on_walls": 0.85}[case]
+    if handed_back.any():
+        slots = np.nonzero(handed_back)[0].astype(np.uint32)
+        e2 = g.clip(work_slots=slots, count=False)
+        _check(e2, g.oracle_cells(slots=slots), "handed back to the warp-per-cell kernel", expect_all=(case != "clustered"))
+
+
+def test_thread_per_cell_kernel_truncated_table_and_thin_halo(eb, gen):
+    """The producers run ahead of the cell builders with a stale (larger) threshold; the end of a truncated table and a
+    missing ghost plane must still be flagged for exactly the cells the reference-shaped walk flags."""
+    pts = gen.uniform(6000, 77)
+    g = eb.EmuGrid(pts, BOX, table_radius=3)  # some cells terminate inside it, the others run off its end
+    a = g.clip(count=False)
+    t = g.clip(large="thread", count=False)
+    exhausted = (a.status & 0x2) != 0
+    assert exhausted.any() and not exhausted.all()
+    same = ~exhausted & ((t.status & 0x2) == 0)  # (the thread kernel also hands back what its tables cannot hold)
+    assert np.array_equal((t.status & 0x2) != 0, exhausted | ((t.status & 0x2) != 0)) and same.sum() > 500
+    assert np.all(((t.status & 0x2) != 0)[exhausted])
+    assert np.array_equal(t.volumes[same], a.volumes[same])
+    # thin halo
+    g = eb.EmuGrid(pts, BOX)
+    lo, hi = g.cpd // 3, g.cpd // 3 + 5
+    ids = g.restrict_to_planes(pts, (lo, hi))
+    cpd = g.cpd
+    gx = g.oracle.cells().astype(np.int64)[ids] // (cpd * cpd)
+    own = np.nonzero((gx >= lo + 1) & (gx < hi - 1))[0].astype(np.uint32)
+    a = g.clip(work_slots=own, count=True)
+    t = g.clip(work_slots=own, count=False, large="thread")
+    done = (t.status & 0x2) == 0
+    assert ((a.status & 0x8) != 0).any() and done.mean() > 0.9
+    assert np.array_equal(t.status[done], a.status[done])
+    assert np.array_equal(t.volumes[done], a.volumes[done])
+
+
+def test_thread_per_cell_kernel_radius_and_group_modes(eb, gen, ob):
+    pts = gen.uniform(3000, 58)
+    groups = (np.arange(len(pts)) % 3).astype(np.uint64)
+    g = eb.EmuGrid(pts, BOX, groups=groups, table_radius=-1)
+    sx = g.cell_info[0]
+    for kw in (dict(search_radius=(1.5 * sx) ** 2), dict(target_group=1), dict(target_group=7)):
+        a = g.clip(count=False, **kw)
+        t = g.clip(large="thread", count=False, **kw)
+        done = (t.status & 0x2) == 0
+        assert done.mean() > 0.9, kw
+        assert np.array_equal(t.status[done], a.status[done]), kw
+        fa, ft = a.face_offsets.astype(np.int64), t.face_offsets.astype(np.int64)
+        assert np.array_equal(np.diff(ft)[done], np.diff(fa)[done]), kw
+        assert np.array_equal(t.volumes[done], a.volumes[done]), kw

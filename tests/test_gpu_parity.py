@@ -467,6 +467,96 @@ def test_config3_ten_million_uniform(tess, gen, ob):
     _full_size_checks(tess, gen, ob, gen.uniform(10_000_000, 3), 72, 5_000)
 
 
+def test_config4_ten_million_clustered(tess, gen, ob):
+    """Config 4 exactly as SURVEY §8d states it: 10M points, seed 4, 20 % uniform background + 32 Gaussian clusters of
+    sigma 0.02.  Every tier of the pipeline runs (wider-table, medium and large redo passes); the oracle sample holds
+    random cells plus the cells with the most faces (those are the ones that outgrew the small tables)."""
+    pts = gen.clustered(10_000_000, 4, k=32, sigma=0.02)
+    n = len(pts)
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=7)
+    st = b.tier_stats()
+    assert st["redo_b"] > 0, st  # medium-path cells exist in this input
+    assert np.all(b.status == 0)
+    assert abs(b.volume_sum() - 1.0) <= 1e-12
+    assert np.all(b.volumes > 0) and np.all(b.areas >= 0)
+    nf = np.diff(b.face_offsets.astype(np.int64))
+    assert nf.max() > 40  # beyond the small configuration's face table
+    rnd = np.unique((gen.u01(74, np.arange(3000, dtype=np.uint64)) * n).astype(np.uint64))
+    big = np.argsort(nf)[-400:].astype(np.uint64)
+    ids = np.unique(np.concatenate([rnd, big]))
+    r = ob.Diagram(pts, box=BOX).compute_cells(ids=ids, mode=ob.MODE_SECURITY)
+    mask = np.zeros(n, bool)
+    mask[ids.astype(np.int64)] = True
+    helpers.assert_cells_identical(_Subset(b, mask), r, what=f"clustered 10M, sample of {len(ids)}")
+    # the counting instantiation and the other main tiers give the same arrays
+    try:
+        for tier, outputs in (("default", ALL_OUT), ("small", 7), ("thread", 7)):
+            tess.set_main_tier(tier)
+            t = d.compute_all_cells(outputs=outputs)
+            for name in ("volumes", "face_offsets", "neighbors", "areas", "status"):
+                assert np.array_equal(getattr(t, name), getattr(b, name)), (tier, name)
+            del t
+    finally:
+        tess.set_main_tier("default")
+    d.close()
+
+
+def test_config5_jittered_bcc_on_one_gpu(tess, gen, ob):
+    """Config 5's input at the size one test can afford (2 * 128^3 = 4.2M points, jitter 1e-3 a): oracle sample bit for
+    bit, and the analytic cell (truncated octahedron: 14 faces, V = a^3 / 2) as an independent anchor — the jitter moves
+    every bisector by O(1e-3 a), so volumes stay within 2e-2 relative and the neighbour sets are the lattice's."""
+    import test_oracle_analytic as an
+
+    m = 128
+    pts = gen.bcc(m, 5)
+    _full_size_checks(tess, gen, ob, pts, 75, 4_000)
+    d = _diagram(tess, pts)
+    b = d.compute_all_cells(outputs=7)
+    a = 1.0 / m
+    fo = b.face_offsets.astype(np.int64)
+    p = np.arange(len(pts), dtype=np.int64)
+    site = p // 2
+    i, j, k = site // (m * m), (site // m) % m, site % m
+    inner = (np.minimum(np.minimum(i, j), k) >= 2) & (np.maximum(np.maximum(i, j), k) <= m - 3)
+    assert np.all(np.diff(fo)[inner] == 14)
+    assert np.max(np.abs(b.volumes[inner] - a ** 3 / 2) / (a ** 3 / 2)) < 2e-2
+    sq, hx = a * a / 8, 3 * np.sqrt(3.0) * a * a / 16
+    for c in np.flatnonzero(inner)[:: 40_000]:
+        nb, ar = b.neighbors[fo[c]:fo[c + 1]], b.areas[fo[c]:fo[c + 1]]
+        same = (nb % 2) == (c % 2)
+        assert same.sum() == 6 and np.all(np.abs(ar[same] - sq) / sq < 5e-2) and np.all(np.abs(ar[~same] - hx) / hx < 5e-2)
+    d.close()
+
+
+def test_analytic_lattices_on_gpu(tess, gen):
+    """The closed forms that pin the oracle (tests/test_oracle_analytic.py), asserted on the GPU's own output: un-jittered
+    BCC (truncated octahedra), simple cubic (cubes) and points on a line (slabs), for every main tier."""
+    import test_oracle_analytic as an
+
+    try:
+        for tier in ("default", "small", "thread"):
+            tess.set_main_tier(tier)
+            m = 16
+            d = _diagram(tess, gen.bcc(m, 5, jitter=0.0))
+            b = d.compute_all_cells(outputs=7, table_radius=1 << 20)
+            assert an.check_bcc(b.volumes, b.face_offsets, b.neighbors, b.areas, b.status, m) > 1.4 * (m - 4) ** 3
+            d.close()
+            m = 12
+            d = _diagram(tess, gen.simple_cubic(m))
+            b = d.compute_all_cells(outputs=7, table_radius=1 << 20)
+            assert an.check_simple_cubic(b.volumes, b.face_offsets, b.neighbors, b.areas, b.status, m) > 0.3 * (m - 2) ** 3
+            d.close()
+            pts, x = an.line_points(gen)
+            d = _diagram(tess, pts)
+            b = d.compute_all_cells(outputs=7)
+            assert np.all(b.status == 0)
+            an.check_line(b.volumes, b.face_offsets, b.neighbors, b.areas, x)
+            d.close()
+    finally:
+        tess.set_main_tier("default")
+
+
 # ------------------------------------------------------------------ geometry (SURVEY §8 f1) ---
 def test_vertices_and_face_loops_match_oracle(tess, gen, ob):
     """Cell::compute_vertices (interface.rs:368) and VoronoiFace::compute_vertices (interface.rs:403 ->

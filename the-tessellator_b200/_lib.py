@@ -31,7 +31,7 @@ SYMBOLS = (
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
     "tess_result_face_vertex_offsets", "tess_result_face_vertex_indices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
-    "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs",
+    "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs", "tess_pack_records", "tess_diagram_add_records_device",
     "tess_find_neighbors", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
     "tess_result_download", "tess_set_main_tier", "tess_result_tier_stats", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
@@ -140,6 +140,8 @@ def lib() -> C.CDLL:
     sig("tess_plane_histogram", ci, vp, sz, vp, u64, vp, vp)
     sig("tess_bounds", ci, vp, sz, vp, vp)
     sig("tess_pack_for_slabs", ci, vp, vp, i64, sz, vp, u64, ci, vp, vp, vp, vp, vp, sz, vp)
+    sig("tess_pack_records", ci, vp, vp, i64, sz, vp, u64, ci, vp, vp, vp, vp, vp, vp, sz, vp)
+    sig("tess_diagram_add_records_device", ci, vp, vp, sz, vp)
     _lib = L
     return L
 

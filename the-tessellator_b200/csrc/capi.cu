@@ -1359,8 +1359,64 @@ int tess_pack_for_slabs(const double* xyz_dev, const int64_t* ids_dev, int64_t i
     if (acc > cap || !out_xyz_dev || !out_ids_dev) return fail(TESS_ERR_NOMEM, "pack buffer too small (send counts are valid)");
     TESS_CUDA_CHECK(cudaMemcpyAsync(offs, ho.data(), sizeof(unsigned long long) * n_ranks, cudaMemcpyHostToDevice, s));
     TESS_CUDA_CHECK(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * n_ranks, s));
-    launch_pack_scatter(xyz_dev, ids_dev, id_base, n, g, n_ranks, lo, hi, offs, cursors, out_xyz_dev, out_ids_dev, s);
+    launch_pack_scatter(xyz_dev, ids_dev, id_base, n, g, n_ranks, lo, hi, offs, nullptr, cursors, out_xyz_dev, out_ids_dev, nullptr, s);
     TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_pack_records(const double* xyz_dev, const int64_t* ids_dev, int64_t id_base, size_t n, const double bounds[6], uint64_t n_global, int n_ranks,
+                      const uint32_t* plane_lo, const uint32_t* plane_hi, const uint64_t* planned_counts, uint64_t* counts_host, uint64_t* counts_dev,
+                      double* out_rec_dev, size_t cap, void* stream) {
+    if (!bounds || !plane_lo || !plane_hi || !counts_dev || n_ranks <= 0 || n_ranks > 1024) return fail(TESS_ERR_INVALID, "bad argument");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GridSpec g = spec_from_bounds(bounds, n_global);
+    Scratch tmp(s);
+    uint32_t* lo = tmp.get<uint32_t>(n_ranks);
+    uint32_t* hi = tmp.get<uint32_t>(n_ranks);
+    unsigned long long* offs = tmp.get<unsigned long long>(2 * n_ranks);  // offsets, then limits
+    TESS_CUDA_CHECK(cudaMemcpyAsync(lo, plane_lo, sizeof(uint32_t) * n_ranks, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemcpyAsync(hi, plane_hi, sizeof(uint32_t) * n_ranks, cudaMemcpyHostToDevice, s));
+    TESS_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * n_ranks, s));
+    std::vector<unsigned long long> hc(n_ranks), ho(2 * n_ranks);
+    if (planned_counts) {
+        // the caller knows the counts (an unchanged particle set): no counting pass, no host round trip.  The scatter's
+        // cursors land in counts_dev; the caller compares them with the plan.
+        for (int r = 0; r < n_ranks; ++r) hc[r] = planned_counts[r];
+    } else {
+        launch_pack_count(xyz_dev, n, g, n_ranks, lo, hi, reinterpret_cast<unsigned long long*>(counts_dev), s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(hc.data(), counts_dev, sizeof(uint64_t) * n_ranks, cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        TESS_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * n_ranks, s));
+    }
+    unsigned long long acc = 0;
+    for (int r = 0; r < n_ranks; ++r) { ho[r] = acc; ho[n_ranks + r] = hc[r]; acc += hc[r]; }
+    if (counts_host) for (int r = 0; r < n_ranks; ++r) counts_host[r] = hc[r];
+    if (acc > cap || !out_rec_dev) return fail(TESS_ERR_NOMEM, "pack buffer too small (counts_host is valid)");
+    TESS_CUDA_CHECK(cudaMemcpyAsync(offs, ho.data(), sizeof(unsigned long long) * 2 * n_ranks, cudaMemcpyHostToDevice, s));
+    launch_pack_scatter(xyz_dev, ids_dev, id_base, n, g, n_ranks, lo, hi, offs, offs + n_ranks, reinterpret_cast<unsigned long long*>(counts_dev), nullptr, nullptr, out_rec_dev, s);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_diagram_add_records_device(tess_diagram* d, const double* rec_dev, size_t n, void* stream) {
+    if (!d || (!rec_dev && n)) return fail(TESS_ERR_INVALID, "NULL argument");
+    if (d->initialized) return fail(TESS_ERR_STATE, "particles must be added before initialize (interface.rs:50-51)");
+    if (d->n + n >= 0xFFFFFFF0ull) return fail(TESS_ERR_INVALID, "more than 2^32 particles on one device");
+    if (d->n && !d->has_ids) return fail(TESS_ERR_INVALID, "ids must be given for all particles or for none");
+    if (d->has_groups) return fail(TESS_ERR_INVALID, "records carry no groups");
+    if (!n) return TESS_OK;
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TESS_CUDA_CHECK(cudaSetDevice(d->device));
+    const size_t n0 = d->n;
+    d->xyz.grow_keep(sizeof(double) * 3 * (n0 + n), sizeof(double) * 3 * n0, s);
+    d->ids.grow_keep(sizeof(int64_t) * (n0 + n), sizeof(int64_t) * n0, s);
+    TESS_CUDA_CHECK(cudaMemcpy2DAsync(d->xyz.as<double>() + 3 * n0, 24, rec_dev, 32, 24, n, cudaMemcpyDeviceToDevice, s));
+    TESS_CUDA_CHECK(cudaMemcpy2DAsync(d->ids.as<int64_t>() + n0, 8, rec_dev + 3, 32, 8, n, cudaMemcpyDeviceToDevice, s));
+    d->has_ids = true;
+    d->n = n0 + n;
     return TESS_OK;
     TESS_CATCH
 }

@@ -129,7 +129,7 @@ struct SmemMask {
 // Configurations
 // ---------------------------------------------------------------------------------------------
 #ifndef TESS_CLIP_MINBLOCKS
-#define TESS_CLIP_MINBLOCKS 5  // resident CTAs per SM the small kernel is compiled for (register cap)
+#define TESS_CLIP_MINBLOCKS 8  // resident CTAs per SM the small kernel is compiled for (64 registers; A/B on 1M uniform: 5 -> 20.75 ms, 6 -> 20.05, 7 -> 19.17, 8 -> 18.59, 9 -> 18.94, 10 -> 20.06)
 #endif
 // A staged tile with at least this many candidates waiting is screened candidate-parallel before the planes
 // are offered one by one (0 disables the screen); see the comment at its use.

@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(kThreads) pack_count_kernel(const double* __re
 
 __global__ void __launch_bounds__(kThreads) pack_scatter_kernel(const double* __restrict__ xyz, const int64_t* __restrict__ ids, int64_t id_base, size_t n, GridSpec g,
                                                                 int n_ranks, const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi,
-                                                                const unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ cursors,
-                                                                double* __restrict__ out_xyz, int64_t* __restrict__ out_ids) {
+                                                                const unsigned long long* __restrict__ offsets, const unsigned long long* __restrict__ limits,
+                                                                unsigned long long* __restrict__ cursors, double* __restrict__ out_xyz, int64_t* __restrict__ out_ids, double* __restrict__ out_rec) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const bool valid = i < n;
     double x = 0, y = 0, z = 0;
@@ -323,10 +323,17 @@ __global__ void __launch_bounds__(kThreads) pack_scatter_kernel(const double* __
         unsigned long long base = 0;
         if (lane == leader) base = atomicAdd(&cursors[r], (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (hit) {
-            const unsigned long long dst = offsets[r] + base + __popc(m & ((1u << lane) - 1u));
-            out_xyz[3 * dst] = x; out_xyz[3 * dst + 1] = y; out_xyz[3 * dst + 2] = z;
-            out_ids[dst] = ids ? ids[i] : id_base + (int64_t)i;
+        const unsigned long long k = base + __popc(m & ((1u << lane) - 1u));
+        if (hit && (!limits || k < limits[r])) {  // (a stale plan's counts may be too small: the excess is dropped, the cursor tells)
+            const unsigned long long dst = offsets[r] + k;
+            const int64_t id = ids ? ids[i] : id_base + (int64_t)i;
+            if (out_rec) {  // one 32-byte record {x, y, z, id}: a single all-to-all carries it
+                double4* q = reinterpret_cast<double4*>(out_rec) + dst;
+                *q = make_double4(x, y, z, __longlong_as_double(id));
+            } else {
+                out_xyz[3 * dst] = x; out_xyz[3 * dst + 1] = y; out_xyz[3 * dst + 2] = z;
+                out_ids[dst] = id;
+            }
         }
     }
 }
@@ -414,9 +421,10 @@ void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ran
 }
 
 void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev,
-                         const unsigned long long* offsets, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, cudaStream_t s) {
+                         const unsigned long long* offsets, const unsigned long long* limits, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, double* out_rec,
+                         cudaStream_t s) {
     if (!n) return;
-    TESS_LAUNCH(pack_scatter_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, ids, id_base, n, g, n_ranks, lo_dev, hi_dev, offsets, cursors, out_xyz, out_ids);
+    TESS_LAUNCH(pack_scatter_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, ids, id_base, n, g, n_ranks, lo_dev, hi_dev, offsets, limits, cursors, out_xyz, out_ids, out_rec);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }

@@ -6,14 +6,21 @@ plus a halo of `h` planes on each side is everything a rank needs.
 
     bounds      all-reduce(min/max) of 6 scalars          -> identical grid parameters everywhere
     histogram   all-reduce(sum) of particles per x-plane  -> equal-count slab cuts
-    exchange    all-to-all(v) of (xyz, id) records        -> every rank receives its owned planes
-                                                             plus the halo planes (ghost particles)
+    exchange    ONE all-to-all(v) of 32-byte {x, y, z, id}   -> every rank receives its owned planes
+                records                                       plus the halo planes (ghost particles)
     compute     tess_diagram_initialize_slab + tess_compute_all on the local planes
     verify      any cell whose search reached a plane outside the halo is flagged
                 (TESS_STATUS_HALO_INSUFFICIENT); the exchange is redone with a wider halo.
 
 Every rank bins with the same global bounds / cpd and orders candidates inside a grid cell by
 global particle id, so per-cell results are bit-identical to the single-GPU run.
+
+A `SlabPlan` (bounds, slab cuts, per-destination exchange counts) comes back with every result.  Handing it
+to the next call tells the pipeline that the particle set is unchanged: the three planning collectives and
+their host round trips are skipped, the pack runs without its counting pass, and the only host
+synchronisation left in the step is the final flag (halo too thin | counts differ from the plan), one
+all-reduce.  A plan that does not match the particles is detected by that flag and the step is redone
+without it.
 
 The compute backend is injected (`SlabBackend`): the product backend drives the CUDA library on
 torch CUDA tensors; the CPU tests inject a numpy backend to exercise this host logic under gloo.
@@ -66,6 +73,19 @@ def receive_ranges(cuts: Sequence[int], halo: int) -> Tuple[List[int], List[int]
 
 
 @dataclass
+class SlabPlan:
+    """What a step learns about an unchanged particle set (compute_sharded(plan=...))."""
+
+    bounds6: np.ndarray
+    cuts: List[int]
+    halo: int
+    send_counts: List[int]
+    recv_counts: List[int]
+    n_local: int
+    n_global: int
+
+
+@dataclass
 class SlabResult:
     """Per-rank outcome: rows are the owned cells in the rank's grid order."""
 
@@ -76,6 +96,8 @@ class SlabResult:
     halo: int
     n_received: int
     rounds: int
+    plan: Optional[SlabPlan] = None
+    halo_ok: bool = True     # False: max_rounds / the whole grid was reached with cells still flagged HALO_INSUFFICIENT
 
 
 class SlabBackend:
@@ -93,8 +115,17 @@ class SlabBackend:
     def pack(self, xyz, id_base: int, bounds6, n_global, lo, hi):  # -> (counts list[int], xyz_packed, ids_packed)
         raise NotImplementedError
 
-    def compute(self, xyz, ids, box, bounds6, n_global, own, local, opts):  # -> (batch, n_owned, any_halo_flag: bool)
+    def compute(self, xyz, ids, box, bounds6, n_global, own, local, opts):  # -> (batch, n_owned, any_halo_flag: bool or 1-element int32 tensor)
         raise NotImplementedError
+
+    # Optional fast path (one record all-to-all, plan reuse).  A backend without it gets the two-array exchange.
+    def pack_records(self, xyz, id_base: int, bounds6, n_global, lo, hi, planned_counts=None):  # -> (counts list[int], records (m, 4) f64, counts_dev int64[R])
+        raise NotImplementedError
+
+    def compute_records(self, rec, box, bounds6, n_global, own, local, opts):  # -> (batch, n_owned, flag tensor int32[1])
+        raise NotImplementedError
+
+    has_records = False
 
 
 class CudaSlabBackend(SlabBackend):
@@ -110,6 +141,7 @@ class CudaSlabBackend(SlabBackend):
         self.device_index = device_index
         self.device = torch.device("cuda", device_index)
         self._diagram = None
+        self._rec_buf = None
 
     def _stream(self) -> int:
         return self._torch.cuda.current_stream(self.device).cuda_stream
@@ -146,7 +178,38 @@ class CudaSlabBackend(SlabBackend):
                 self._lib.check(rc)
             cap = sum(c) + 1024
 
+    has_records = True
+
+    def pack_records(self, xyz, id_base, bounds6, n_global, lo, hi, planned_counts=None):
+        torch = self._torch
+        n, R = xyz.shape[0], len(lo)
+        b = np.ascontiguousarray(bounds6, dtype=np.float64)
+        plo, phi = np.ascontiguousarray(lo, dtype=np.uint32), np.ascontiguousarray(hi, dtype=np.uint32)
+        counts_dev = torch.empty(R, dtype=torch.int64, device=self.device)
+        hc = np.zeros(R, dtype=np.uint64)
+        plan = None if planned_counts is None else np.ascontiguousarray(planned_counts, dtype=np.uint64)
+        cap = (int(plan.sum()) if plan is not None else int(n * 1.5)) + 1024
+        while True:
+            if self._rec_buf is None or self._rec_buf.shape[0] < cap:
+                self._rec_buf = torch.empty((cap, 4), dtype=torch.float64, device=self.device)
+            rc = self._lib.lib().tess_pack_records(xyz.data_ptr(), None, id_base, n, b.ctypes.data, n_global, R, plo.ctypes.data, phi.ctypes.data,
+                                                   None if plan is None else plan.ctypes.data, hc.ctypes.data, counts_dev.data_ptr(), self._rec_buf.data_ptr(),
+                                                   self._rec_buf.shape[0], self._stream())
+            c = [int(v) for v in hc]
+            if rc == 0:
+                return c, self._rec_buf[: sum(c)], counts_dev
+            if rc != -4:
+                self._lib.check(rc)
+            cap = sum(c) + 1024
+
+    def compute_records(self, rec, box, bounds6, n_global, own, local, opts):
+        return self._compute(None, None, rec, box, bounds6, n_global, own, local, opts)
+
     def compute(self, xyz, ids, box, bounds6, n_global, own, local, opts):
+        batch, n_owned, flag = self._compute(xyz, ids, None, box, bounds6, n_global, own, local, opts)
+        return batch, n_owned, bool(flag.item())
+
+    def _compute(self, xyz, ids, rec, box, bounds6, n_global, own, local, opts):
         from .interface import Polyhedron
 
         if self._diagram is None:
@@ -154,7 +217,10 @@ class CudaSlabBackend(SlabBackend):
         d = self._diagram
         d.clear()
         s = self._stream()
-        d.add_particles_device(xyz.data_ptr(), xyz.shape[0], ids_ptr=ids.data_ptr(), stream=s)
+        if rec is not None:
+            d.add_records_device(rec.data_ptr(), rec.shape[0], stream=s)
+        else:
+            d.add_particles_device(xyz.data_ptr(), xyz.shape[0], ids_ptr=ids.data_ptr(), stream=s)
         d.initialize_slab(Polyhedron(*box), bounds6, n_global, own, local, stream=s)
         opts = dict(opts)
         sink = opts.pop("host_sink", None)
@@ -162,12 +228,12 @@ class CudaSlabBackend(SlabBackend):
             batch = d.compute_all_cells(stream=s, **opts)
         else:  # (volumes, face_offsets, neighbors, areas, status[, n_chunks]): results stream to the rank's host arrays
             batch = d.compute_all_cells_to_host(*sink[:5], n_chunks=(sink[5] if len(sink) > 5 else 0), stream=s, **opts)
-        flagged = False
+        flag = self._torch.zeros(1, dtype=self._torch.int32, device=self.device)
         if batch.n_cells:
-            # status words stay on the device: one tiny reduction tells whether any halo was too thin
+            # status words stay on the device, and so does the answer: one tiny reduction tells whether any halo was too thin
             st = _as_tensor(self._torch, batch.device_views()["status"], batch.n_cells, self._torch.int32, self.device)
-            flagged = bool(((st & self._lib.STATUS_HALO_INSUFFICIENT) != 0).any().item())
-        return batch, batch.n_cells, flagged
+            flag = ((st & self._lib.STATUS_HALO_INSUFFICIENT) != 0).any().to(self._torch.int32).reshape(1)
+        return batch, batch.n_cells, flag
 
 
 def _as_tensor(torch, ptr: int, n: int, dtype, device):
@@ -185,60 +251,99 @@ def _as_tensor(torch, ptr: int, n: int, dtype, device):
 
 
 def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int, box: Sequence[float], dist=None, halo: int = 4,
-                    max_rounds: int = 4, opts: Optional[dict] = None, bounds6: Optional[np.ndarray] = None) -> SlabResult:
+                    max_rounds: int = 4, opts: Optional[dict] = None, bounds6: Optional[np.ndarray] = None, plan: Optional[SlabPlan] = None) -> SlabResult:
     """Run the sharded hot path on this rank.
 
     xyz_local : (n_local, 3) f64 tensor on the backend's device — an arbitrary subset of the global
                 particle set (global ids id_base .. id_base+n_local-1).
     dist      : torch.distributed (initialised) or None for a single process.
+    plan      : the `plan` of an earlier result over the SAME particles (all ranks pass one, or none does).
     """
     import torch
 
     opts = dict(opts or {})
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
-
-    # ---- global bounds: CeleryBounds::new (celery.rs:81-125) over ALL particles ---------------
-    if bounds6 is None:
-        b = backend.bounds(xyz_local)
-        if dist is not None and world > 1:
-            mins, maxs = b[0::2].clone(), b[1::2].clone()
-            dist.all_reduce(mins, op=dist.ReduceOp.MIN)
-            dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
-            b = torch.stack([mins, maxs], dim=1).reshape(-1)
-        bounds6 = b.cpu().numpy().astype(np.float64)
+    multi = dist is not None and world > 1
+    n_local = int(xyz_local.shape[0])
+    if plan is not None and (plan.n_local != n_local or plan.n_global != n_global or len(plan.cuts) != world + 1 or not backend.has_records):
+        raise ValueError("compute_sharded: the plan was made for another particle set / world size")
     cpd = cells_per_dimension(n_global)
 
-    # ---- equal-count slab cuts from the per-plane histogram ----------------------------------
-    hist = backend.plane_histogram(xyz_local, bounds6, n_global)
-    if dist is not None and world > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-    cuts = slab_cuts(hist.cpu().numpy(), world)
+    if plan is None:
+        # ---- global bounds: CeleryBounds::new (celery.rs:81-125) over ALL particles: one all-reduce (max of {-min, max})
+        if bounds6 is None:
+            b = backend.bounds(xyz_local)
+            if multi:
+                mm = torch.cat([-b[0::2], b[1::2]])
+                dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+                b = torch.stack([-mm[:3], mm[3:]], dim=1).reshape(-1)
+            bounds6 = b.cpu().numpy().astype(np.float64)
+        # ---- equal-count slab cuts from the per-plane histogram ----------------------------------
+        hist = backend.plane_histogram(xyz_local, bounds6, n_global)
+        if multi:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        cuts = slab_cuts(hist.cpu().numpy(), world)
+    else:
+        bounds6, cuts, halo = plan.bounds6, plan.cuts, plan.halo
 
     rounds = 0
     while True:
         rounds += 1
         lo, hi = receive_ranges(cuts, halo)
-        # ---- ghost-particle exchange: all-to-all(v) of (xyz, id) -----------------------------
-        send_counts, sxyz, sids = backend.pack(xyz_local, id_base, bounds6, n_global, lo, hi)
-        if dist is not None and world > 1:
-            sc = torch.tensor(send_counts, dtype=torch.int64, device=sxyz.device)
-            rc = torch.empty_like(sc)
-            dist.all_to_all_single(rc, sc)
-            recv_counts = [int(v) for v in rc.cpu().tolist()]
-            rxyz = torch.empty((sum(recv_counts), 3), dtype=sxyz.dtype, device=sxyz.device)
-            rids = torch.empty(sum(recv_counts), dtype=sids.dtype, device=sids.device)
-            dist.all_to_all_single(rxyz, sxyz, output_split_sizes=recv_counts, input_split_sizes=send_counts)
-            dist.all_to_all_single(rids, sids, output_split_sizes=recv_counts, input_split_sizes=send_counts)
-        else:
-            rxyz, rids = sxyz, sids
         own = (cuts[rank], cuts[rank + 1])
         local = (lo[rank], hi[rank])
-        batch, n_owned, flagged = backend.compute(rxyz, rids, box, bounds6, n_global, own, local, opts)
-        # ---- was any halo too thin? ----------------------------------------------------------
-        flag = torch.tensor([1 if flagged else 0], dtype=torch.int32, device=rxyz.device)
-        if dist is not None and world > 1:
+        mismatch = None
+        if backend.has_records:
+            # ---- ghost-particle exchange: ONE all-to-all(v) of 32-byte records ---------------------
+            planned = plan.send_counts if plan is not None else None
+            send_counts, srec, counts_dev = backend.pack_records(xyz_local, id_base, bounds6, n_global, lo, hi, planned)
+            if multi:
+                if plan is not None:
+                    recv_counts = plan.recv_counts
+                    mismatch = (counts_dev != torch.tensor(send_counts, dtype=torch.int64, device=counts_dev.device)).any().to(torch.int32).reshape(1)
+                else:
+                    sc = torch.tensor(send_counts, dtype=torch.int64, device=srec.device)
+                    rc = torch.empty_like(sc)
+                    dist.all_to_all_single(rc, sc)
+                    recv_counts = [int(v) for v in rc.cpu().tolist()]
+                rrec = torch.empty((sum(recv_counts), 4), dtype=srec.dtype, device=srec.device)
+                dist.all_to_all_single(rrec, srec, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+            else:
+                rrec, recv_counts = srec, list(send_counts)
+            batch, n_owned, flag = backend.compute_records(rrec, box, bounds6, n_global, own, local, opts)
+            n_received = int(rrec.shape[0])
+            flag = flag.to(torch.int32).reshape(1)
+        else:
+            send_counts, sxyz, sids = backend.pack(xyz_local, id_base, bounds6, n_global, lo, hi)
+            if multi:
+                sc = torch.tensor(send_counts, dtype=torch.int64, device=sxyz.device)
+                rc = torch.empty_like(sc)
+                dist.all_to_all_single(rc, sc)
+                recv_counts = [int(v) for v in rc.cpu().tolist()]
+                rxyz = torch.empty((sum(recv_counts), 3), dtype=sxyz.dtype, device=sxyz.device)
+                rids = torch.empty(sum(recv_counts), dtype=sids.dtype, device=sids.device)
+                dist.all_to_all_single(rxyz, sxyz, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+                dist.all_to_all_single(rids, sids, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+            else:
+                rxyz, rids, recv_counts = sxyz, sids, list(send_counts)
+            batch, n_owned, flagged = backend.compute(rxyz, rids, box, bounds6, n_global, own, local, opts)
+            n_received = int(rxyz.shape[0])
+            flag = torch.tensor([1 if flagged else 0], dtype=torch.int32, device=rxyz.device)
+        # ---- was any halo too thin (bit 0)?  did the particles differ from the plan (bit 1)?  One all-reduce, one read.
+        if mismatch is not None:
+            flag = flag | (mismatch << 1)
+        if multi:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()) == 0 or rounds >= max_rounds or halo >= cpd:
-            return SlabResult(batch=batch, own=own, local=local, n_owned=n_owned, halo=halo, n_received=int(rxyz.shape[0]), rounds=rounds)
-        halo = min(cpd, 2 * halo)
+        f = int(flag.item())
+        if f & 2:
+            # the caller's promise did not hold: plan again from scratch
+            if hasattr(batch, "close"):
+                batch.close()
+            return compute_sharded(backend, xyz_local, id_base, n_global, box, dist=dist, halo=halo, max_rounds=max_rounds, opts=opts, plan=None)
+        done = (f & 1) == 0
+        if done or rounds >= max_rounds or halo >= cpd:
+            new_plan = SlabPlan(bounds6=bounds6, cuts=list(cuts), halo=halo, send_counts=list(send_counts), recv_counts=list(recv_counts), n_local=n_local, n_global=n_global)
+            return SlabResult(batch=batch, own=own, local=local, n_owned=n_owned, halo=halo, n_received=n_received, rounds=rounds, plan=new_plan, halo_ok=done)
+        halo = cpd if rounds + 1 >= max_rounds else min(cpd, 2 * halo)  # the last round takes every plane: it cannot be flagged
+        plan = None

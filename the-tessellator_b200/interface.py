@@ -225,6 +225,12 @@ class Diagram:
         check(_lib.lib().tess_diagram_add_particles_device(self._h, xyz_ptr, n, groups_ptr or None, ids_ptr or None, stream))
         self._n += n
 
+    def add_records_device(self, rec_ptr: int, n: int, stream: int = 0) -> None:
+        """Particles resident in device memory as 32-byte records {x, y, z, id} (tess_pack_records after the exchange)."""
+        self._flush()
+        check(_lib.lib().tess_diagram_add_records_device(self._h, rec_ptr, n, stream))
+        self._n += n
+
     def _position_of(self, index: int):
         for lo, a in self._host_pts:
             if lo <= index < lo + a.shape[0]:

@@ -13,6 +13,12 @@ for f in capi grid outputs query clip clip_thread; do
   fi
 done
 wait
-nvcc $FLAGS "$@" -Xptxas -v -c clip_thread.cu -o $OUT/obj/clip_thread_$name.o 2>&1 | grep -E "registers|spill" | head -4
-nvcc $FLAGS -shared -o $OUT/libtess_$name.so $OUT/obj/capi.o $OUT/obj/grid.o $OUT/obj/outputs.o $OUT/obj/query.o $OUT/obj/clip.o $OUT/obj/clip_thread_$name.o -lcudart
+# AB_SRC=clip builds the variant of clip.cu instead of clip_thread.cu
+src=${AB_SRC:-clip_thread}
+nvcc $FLAGS "$@" -Xptxas -v -c $src.cu -o $OUT/obj/${src}_$name.o 2>&1 | grep -E "Compiling entry|registers|spill" | grep -A2 -E "${AB_GREP:-.}" | cut -c1-160 | head -${AB_LINES:-4}
+objs=""
+for f in capi grid outputs query clip clip_thread; do
+  if [ $f = $src ]; then objs="$objs $OUT/obj/${f}_$name.o"; else objs="$objs $OUT/obj/$f.o"; fi
+done
+nvcc $FLAGS -shared -o $OUT/libtess_$name.so $objs -lcudart
 echo built $OUT/libtess_$name.so

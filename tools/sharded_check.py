@@ -36,7 +36,18 @@ def main():
     xyz = torch.from_numpy(pts[start:start + cnt]).to(dev)
     be = D.CudaSlabBackend(lr)
     res = D.compute_sharded(be, xyz, start, n, [0, 0, 0, 1, 1, 1], dist=dist, halo=4, opts=dict(outputs=7))
+    assert res.halo_ok
     b = res.batch
+    first = [a.copy() for a in (b.cell_ids, b.volumes, b.face_offsets, b.neighbors, b.areas, b.status)]
+    # the same particles again with the first step's plan (no planning collectives, one record all-to-all)
+    res2 = D.compute_sharded(be, xyz, start, n, [0, 0, 0, 1, 1, 1], dist=dist, opts=dict(outputs=7), plan=res.plan)
+    b2 = res2.batch
+    same = all(np.array_equal(x, y) for x, y in zip(first, (b2.cell_ids, b2.volumes, b2.face_offsets, b2.neighbors, b2.areas, b2.status))) and res2.rounds == 1
+    t_same = torch.tensor([1 if same else 0], device=dev)
+    dist.all_reduce(t_same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"planned step bit-identical = {bool(t_same.item())}", flush=True)
+    b = b2
     ids = torch.from_numpy(b.cell_ids.copy()).to(dev)
     vol = torch.from_numpy(b.volumes.copy()).to(dev)
     cnts = torch.from_numpy(np.diff(b.face_offsets)).to(dev)
