@@ -276,6 +276,23 @@ def test_reference_radius_mode(tess, gen, ob):
     d.close()
 
 
+def test_reference_radius_beyond_the_default_table(tess, gen, ob):
+    """a radius that reaches past the default search table (half-width 8 grid cells).  The table is sized from
+    the radius, and a caller-given table that is too small is widened by the redo passes — never silently cut short."""
+    pts = gen.uniform(6000, 59)
+    d = _diagram(tess, pts)
+    od = ob.Diagram(pts, box=BOX)
+    sx = od.cell_info()[0]
+    radius = (9.5 * sx) ** 2
+    r = od.compute_cells(mode=ob.MODE_REFERENCE_RADIUS, search_radius=radius)
+    for kw in (dict(), dict(table_radius=4)):
+        b = d.compute_all_cells(search_radius=radius, outputs=ALL_OUT, **kw)
+        helpers.assert_cells_identical(b, r, what=f"radius {radius} {kw}")
+        assert np.all(b.status == 0)
+    assert d.compute_all_cells(search_radius=radius, outputs=ALL_OUT).counters()["tested"] == r.counters["tested"]
+    d.close()
+
+
 def test_target_group(tess, gen, ob):
     pts = gen.uniform(20_000, 58)
     groups = (np.arange(len(pts)) % 3).astype(np.uint64)
@@ -302,6 +319,31 @@ def test_cells_at_query_points(tess, gen, ob):
         r = od.compute_cell_at_point(*q[i])
         assert b.cell_neighbors(i).tolist() == r.neighbors.tolist()
         assert b.volumes[i] == r.volumes[0] and np.array_equal(b.cell_areas(i), r.areas)
+    d.close()
+
+
+def test_query_cells_take_the_redo_tiers(tess, gen, ob):
+    """cells at query positions (get_cell_at_particle, interface.rs:211-232) that the small tables or the default
+    search table cannot finish — a position inside a dense shell (hundreds of faces), a position in a void (the walk runs
+    off the radius-8 table) — are redone tier by tier like every other cell, not returned empty or half clipped."""
+    u = gen.uniform(300, 54)
+    th, ph = np.arccos(2 * u[:, 0] - 1), 2 * np.pi * u[:, 1]
+    shell = 0.5 + 0.3 * np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], axis=1)
+    bg = gen.uniform(60_000, 55)
+    pts = np.concatenate([shell, bg[(np.linalg.norm(bg - 0.5, axis=1) > 0.35)]])  # a shell around an empty ball, a dense background outside
+    d = _diagram(tess, pts)
+    od = ob.Diagram(pts, box=BOX)
+    q = np.concatenate([[[0.5, 0.5, 0.5], [0.52, 0.47, 0.5]], gen.uniform(20, 60)])
+    b = d.compute_cells_at(q, outputs=ALL_OUT)
+    assert np.all(b.status == 0)
+    for i in range(len(q)):
+        r = od.compute_cell_at_point(*q[i])
+        assert b.cell_neighbors(i).tolist() == r.neighbors.tolist(), i
+        assert b.volumes[i] == r.volumes[0] and np.array_equal(b.cell_areas(i), r.areas), i
+    assert len(b.cell_neighbors(0)) > 100
+    # the per-cell API on the same position
+    cell = d.get_cell_at_particle((0.5, 0.5, 0.5), tess.Polyhedron(*BOX))
+    assert cell.compute_volume() == od.compute_cell_at_point(0.5, 0.5, 0.5).volumes[0]
     d.close()
 
 

@@ -609,7 +609,18 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     }
     const bool query = query_host != nullptr;
     const size_t n_rows = query ? n_query : static_cast<size_t>(d->own_slot_end - d->own_slot_begin);
-    const int R0 = o.table_radius > 0 ? o.table_radius : kDefaultTableRadius;
+    int R0 = o.table_radius > 0 ? o.table_radius : kDefaultTableRadius;
+    if (!(o.search_radius != o.search_radius) && o.table_radius <= 0) {
+        // reference-radius mode (expand_all_in_radius, celery.rs:1036) walks every table entry with key <= radius: the table
+        // must hold them all, (R * size)^2 > radius on every axis — the sizing tess_find_neighbors uses
+        const double smin = std::min(d->grid.sx, std::min(d->grid.sy, d->grid.sz));
+        int R = static_cast<int>(d->grid.cpd);  // full table
+        if (o.search_radius >= 0 && smin > 0) {
+            const double need = std::sqrt(o.search_radius) / smin + 2.0;
+            if (need < static_cast<double>(d->grid.cpd)) R = std::max(1, static_cast<int>(need));
+        }
+        R0 = std::max(R0, R);
+    }
     const bool want_area = (o.outputs & TESS_OUT_AREAS) != 0;
     const bool want_vtx = (o.outputs & TESS_OUT_VERTICES) != 0;
     const bool want_cnt = (o.outputs & TESS_OUT_COUNTERS) != 0;
@@ -679,7 +690,7 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     P.table_full = tab.full ? 1u : 0u;
     P.grid = d->grid;
     std::memcpy(P.box, d->box, sizeof(P.box));
-    P.slot_begin = d->own_slot_begin;
+    P.slot_begin = query ? 0u : d->own_slot_begin;
     P.n_work = static_cast<uint32_t>(n_rows);
     P.work_slots = nullptr;
     P.query_xyz = query_dev;
@@ -687,14 +698,14 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     if (o.target_group >= 0 && !d->has_groups) P.target_group = (o.target_group == 0) ? -1 : -2;  // -2: nothing matches
     P.search_radius = o.search_radius;
     P.row_of_slot = (d->slab || query) ? nullptr : d->sorted_idx.as<uint32_t>();
-    P.row_base = d->own_slot_begin;
+    P.row_base = query ? 0u : d->own_slot_begin;  // (query cells: work items are query indices, row = index)
     P.vol = r->vol; P.nfaces = r->nfaces; P.status = r->status; P.cell_id = r->cell_id;
     P.st_nbr = st_nbr; P.st_area = st_area; P.fstride = fstride; P.stage_by_work = 0;
     P.gv_xyz = gv_xyz; P.gl_idx = gl_idx; P.gv_cap = gv_cap; P.gl_cap = gl_cap; P.g_cursor = g_cursor;
     P.nverts = r->nverts; P.nloops = nloops; P.vbase = vbase; P.lbase = lbase; P.st_flen = st_flen;
     P.counters = want_cnt ? r->counters : nullptr;
     P.work_counter = ctrl;
-    P.failed_slots = query ? nullptr : failed;
+    P.failed_slots = failed;  // query cells too: what the small tables / the default table cannot finish is redone tier by tier
     P.n_failed = ctrl + 1;
     P.failed_cap = static_cast<uint32_t>(n_rows);
     P.mark_large = 0;

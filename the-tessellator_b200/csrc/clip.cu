@@ -1050,15 +1050,17 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
 
         // ---- the cell's particle (Diagram::get_cell_at_index, interface.rs:193-207) -----------
         uint32_t self_slot = 0xFFFFFFFFu;
+        uint32_t item;  // what the work lists hold: the cell's sorted slot, or the index of its query position
         int hx, hy, hz;
         {
             double px, py, pz;
+            item = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
             if (P.query_xyz) {  // get_cell_at_particle (interface.rs:218-231): no self exclusion
-                px = P.query_xyz[3 * (size_t)work];
-                py = P.query_xyz[3 * (size_t)work + 1];
-                pz = P.query_xyz[3 * (size_t)work + 2];
+                px = P.query_xyz[3 * (size_t)item];
+                py = P.query_xyz[3 * (size_t)item + 1];
+                pz = P.query_xyz[3 * (size_t)item + 2];
             } else {
-                self_slot = P.work_slots ? P.work_slots[work] : P.slot_begin + work;
+                self_slot = item;
                 const double2* q = reinterpret_cast<const double2*>(P.sorted + self_slot);
                 const double2 a = __ldg(q), b = __ldg(q + 1);
                 px = a.x; py = a.y; pz = b.x;
@@ -1260,7 +1262,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     c_tab += __popc(__ballot_sync(FULL, tvalid));
                 }
                 if (!done && t0 + 32 >= P.table_len) {
-                    if (!P.table_full && !radius_mode) status |= ST_TABLE_EXHAUSTED;
+                    if (!P.table_full) status |= ST_TABLE_EXHAUSTED;  // (both modes: a table that ends before a key exceeds the threshold has to be widened)
                     done = true;
                 }
             } else if (!failed) {
@@ -1278,8 +1280,8 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         double vol_part = 0.0;
         uint32_t rank_base = 0;
         // output row of this cell (recomputed here rather than kept live through the cuts)
-        size_t row = work;
-        long long self_id = (long long)work;
+        size_t row = (size_t)(item - P.row_base);
+        long long self_id = (long long)item;
         if (!P.query_xyz) {
             self_id = __double_as_longlong(__ldg(reinterpret_cast<const double*>(P.sorted + self_slot) + 3));
             row = P.row_of_slot ? P.row_of_slot[self_slot] : (size_t)(self_slot - P.row_base);
@@ -1428,9 +1430,9 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
         if (lane == 0) {
             // cells this configuration cannot finish are queued for the large-cell / larger-table pass
             const bool bad = (status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT | ST_TABLE_EXHAUSTED)) != 0;
-            if (bad && P.failed_slots && !P.query_xyz) {
+            if (bad && P.failed_slots) {
                 const uint32_t k = atomicAdd(P.n_failed, 1u);
-                if (k < P.failed_cap) P.failed_slots[k] = self_slot;
+                if (k < P.failed_cap) P.failed_slots[k] = item;
                 // cells that only ran out of search table (a wider table in the same configuration will do)
                 if ((status & (ST_CAPACITY_OVERFLOW | ST_INCONSISTENT)) == 0) atomicAdd(P.n_failed + 4, 1u);
             }

@@ -499,7 +499,7 @@ __device__ void producer_warp(const ClipParams& P, ThreadShared* S, const int pw
                 bool ok = p < total;
                 if (ok) {
                     if (is_end) {
-                        item = (ti0 + (uint32_t)s_lane < P.table_len || P.table_full || radius_mode) ? Q_END : Q_END_EXH;
+                        item = (ti0 + (uint32_t)s_lane < P.table_len || P.table_full) ? Q_END : Q_END_EXH;
                     } else if (e_halo) {
                         item = Q_HALO | (ti0 + (uint32_t)en);
                     } else {

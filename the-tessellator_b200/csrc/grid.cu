@@ -271,7 +271,12 @@ __global__ void __launch_bounds__(kThreads) rank_fix_kernel(const Particle* __re
     const uint32_t c = local_cell(a.x, a.y, b.x, g, oob);
     const uint32_t d0 = __ldg(delim + c), d1 = __ldg(delim + c + 1);
     uint32_t r = 0;
-    for (uint32_t t = d0; t < d1; ++t) r += (arrived[t].id < my) ? 1u : 0u;
+    // ids are unique unless the caller supplied duplicates (add_particles_device(ids_dev)): ties break on the arrival slot, so
+    // that two records never land on the same sorted slot
+    for (uint32_t t = d0; t < d1; ++t) {
+        const int64_t id = arrived[t].id;
+        r += (id < my || (id == my && t < (uint32_t)s)) ? 1u : 0u;
+    }
     const uint32_t dst = d0 + r;
     double2* o = reinterpret_cast<double2*>(sorted + dst);
     o[0] = a;

@@ -259,6 +259,9 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
     dist      : torch.distributed (initialised) or None for a single process.
     plan      : the `plan` of an earlier result over the SAME particles (all ranks pass one, or none does).
     """
+    import os
+    import time
+
     import torch
 
     opts = dict(opts or {})
@@ -266,6 +269,19 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
     rank = dist.get_rank() if dist is not None else 0
     multi = dist is not None and world > 1
     n_local = int(xyz_local.shape[0])
+    # TESS_SHARD_TRACE=1: synchronise after every phase and print where the step's time goes (rank 0; development aid)
+    trace = [] if os.environ.get("TESS_SHARD_TRACE") else None
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if trace is None:
+            return
+        if hasattr(torch, "cuda") and torch.cuda.is_available() and getattr(backend, "device", None) is not None and backend.device.type == "cuda":
+            torch.cuda.synchronize(backend.device)
+        now = time.perf_counter()
+        trace.append((name, (now - t_last[0]) * 1e3))
+        t_last[0] = now
+
     if plan is not None and (plan.n_local != n_local or plan.n_global != n_global or len(plan.cuts) != world + 1 or not backend.has_records):
         raise ValueError("compute_sharded: the plan was made for another particle set / world size")
     cpd = cells_per_dimension(n_global)
@@ -284,6 +300,7 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
         if multi:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM)
         cuts = slab_cuts(hist.cpu().numpy(), world)
+        mark("plan (bounds, histogram, cuts)")
     else:
         bounds6, cuts, halo = plan.bounds6, plan.cuts, plan.halo
 
@@ -298,6 +315,7 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
             # ---- ghost-particle exchange: ONE all-to-all(v) of 32-byte records ---------------------
             planned = plan.send_counts if plan is not None else None
             send_counts, srec, counts_dev = backend.pack_records(xyz_local, id_base, bounds6, n_global, lo, hi, planned)
+            mark("pack")
             if multi:
                 if plan is not None:
                     recv_counts = plan.recv_counts
@@ -311,7 +329,9 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
                 dist.all_to_all_single(rrec, srec, output_split_sizes=recv_counts, input_split_sizes=send_counts)
             else:
                 rrec, recv_counts = srec, list(send_counts)
+            mark("exchange")
             batch, n_owned, flag = backend.compute_records(rrec, box, bounds6, n_global, own, local, opts)
+            mark("bin + clip + outputs")
             n_received = int(rrec.shape[0])
             flag = flag.to(torch.int32).reshape(1)
         else:
@@ -336,6 +356,9 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
         if multi:
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
         f = int(flag.item())
+        mark("flag all-reduce")
+        if trace is not None and rank == 0:
+            print("[shard trace] " + " | ".join(f"{k} {v:.3f} ms" for k, v in trace) + f" | clip kernel {batch.timings()['clip_ms']:.3f} redo {batch.timings()['redo_ms']:.3f} outputs {batch.timings()['outputs_ms']:.3f} ms", flush=True)
         if f & 2:
             # the caller's promise did not hold: plan again from scratch
             if hasattr(batch, "close"):

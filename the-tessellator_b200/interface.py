@@ -436,6 +436,14 @@ class Cell:
     def _need(self) -> CellBatch:
         if self._batch is None:
             self.compute_voronoi_cell()
+            # a cell no tier could finish (more than 1024 vertices / 512 faces, an inconsistent mesh, a search table the
+            # redo passes could not widen enough) has no geometry to hand out: say so instead of returning volume 0
+            st = int(self._batch.status[self._row])
+            bad = st & (_lib.STATUS_TABLE_EXHAUSTED | _lib.STATUS_CAPACITY_OVERFLOW | _lib.STATUS_INCONSISTENT)
+            if bad:
+                raise _lib.TessError(-6, f"cell could not be completed (status 0x{st:x}: " + ", ".join(
+                    n for b, n in ((_lib.STATUS_TABLE_EXHAUSTED, "search table exhausted"), (_lib.STATUS_CAPACITY_OVERFLOW, "mesh tables overflowed"),
+                                   (_lib.STATUS_INCONSISTENT, "inconsistent mesh")) if st & b) + ")")
         return self._batch
 
     def compute_volume(self) -> float:
