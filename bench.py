@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="uniform10m", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override the number of points (development only)")
+    ap.add_argument("--n", "--points", dest="n", type=int, default=0, help="override the number of points (development only; under torchrun spell it --points)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="cells per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

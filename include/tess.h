@@ -198,6 +198,23 @@ enum {
 /* m query positions (host, packed f64 triples) -> CSR lists of particle ids in the reference's order.
  * Whole-domain diagrams only. */
 int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, void* stream, tess_query** out);
+/* Celery::find_cells_in_radius (celery.rs:753-797): per query position the ids (x*cpd^2 + y*cpd + z, celery.rs:317-325) of the
+ * grid cells whose cell distance to the position's cell is within `radius`, in the reference's i, j, k loop order.  The
+ * result's indices are grid cell ids, not particle ids. */
+int tess_find_cells_in_radius(const tess_diagram* d, const double* xyz, size_t m, double radius, void* stream, tess_query** out);
+
+/* ExpandingSearch (celery.rs:865-1075) as an object: one cursor (current_search_index, celery.rs:873) per position.
+ * tess_search_create = ExpandingSearch::new (celery.rs:882-902) for m positions (host, packed f64 triples).
+ * tess_search_expand = ExpandingSearch::expand(max_radius, cells_to_add) (celery.rs:907-963) for all of them at once: walks
+ * at most cells_to_add search-table entries from each cursor on (entries outside the grid count), stops before the first
+ * entry whose squared key exceeds max_radius, appends the particles of the visited cells (original indices, sorted order
+ * within a cell) and leaves the cursors where the walks stopped.  expand_all_in_radius(r) = expand(r, UINT64_MAX) on a
+ * fresh search; expand_all_no_radius = expand(+inf, UINT64_MAX) (celery.rs:971-1018). */
+typedef struct tess_search tess_search;
+int tess_search_create(const tess_diagram* d, const double* xyz, size_t m, tess_search** out);
+int tess_search_expand(tess_search* s, double max_radius, uint64_t cells_to_add, void* stream, tess_query** out);
+int tess_search_cursor(const tess_search* s, const uint64_t** current_search_index);
+void tess_search_free(tess_search* s);
 void tess_query_free(tess_query* q);
 int tess_query_offsets(tess_query* q, const uint64_t** out);  /* m+1 */
 int tess_query_indices(tess_query* q, const int64_t** out);   /* offsets[m] particle ids */

@@ -14,6 +14,10 @@ pub struct tess_result {
 pub struct tess_query {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct tess_search {
+    _private: [u8; 0],
+}
 
 pub const TESS_OK: c_int = 0;
 pub const TESS_F64: c_int = 0;
@@ -68,6 +72,12 @@ extern "C" {
     // radius / neighbour-cloud queries (celery.rs:802-855, :1023-1075; interface.rs:348-365)
     pub fn tess_find_neighbors(d: *const tess_diagram, xyz: *const f64, m: usize, radius: f64, mode: c_int, target_group: i64, stream: *mut c_void,
                                out: *mut *mut tess_query) -> c_int;
+    pub fn tess_find_cells_in_radius(d: *const tess_diagram, xyz: *const f64, m: usize, radius: f64, stream: *mut c_void, out: *mut *mut tess_query) -> c_int;
+    // ExpandingSearch (celery.rs:865-1075)
+    pub fn tess_search_create(d: *const tess_diagram, xyz: *const f64, m: usize, out: *mut *mut tess_search) -> c_int;
+    pub fn tess_search_expand(s: *mut tess_search, max_radius: f64, cells_to_add: u64, stream: *mut c_void, out: *mut *mut tess_query) -> c_int;
+    pub fn tess_search_cursor(s: *const tess_search, current_search_index: *mut *const u64) -> c_int;
+    pub fn tess_search_free(s: *mut tess_search);
     pub fn tess_query_free(q: *mut tess_query);
     pub fn tess_query_offsets(q: *mut tess_query, out: *mut *const u64) -> c_int;
     pub fn tess_query_indices(q: *mut tess_query, out: *mut *const i64) -> c_int;

@@ -55,6 +55,7 @@ fn check(rc: i32) {
 
 struct Batch {
     r: *mut ffi::tess_result,
+    has_vertices: bool,
     volumes: *const f64,
     face_offsets: *const u64,
     neighbors: *const i64,
@@ -128,7 +129,7 @@ impl<PointType: ToCeleryPoint<f64>> Diagram<PointType> {
         self.initialized = true;
     }
 
-    fn opts(search_radius: Option<f64>, target_group: Option<usize>) -> ffi::tess_opts {
+    fn opts(search_radius: Option<f64>, target_group: Option<usize>, vertices: bool) -> ffi::tess_opts {
         let mut o = std::mem::MaybeUninit::<ffi::tess_opts>::uninit();
         let mut o = unsafe {
             ffi::tess_opts_default(o.as_mut_ptr());
@@ -140,13 +141,17 @@ impl<PointType: ToCeleryPoint<f64>> Diagram<PointType> {
         if let Some(g) = target_group {
             o.target_group = g as i64;
         }
-        // Cell::compute_vertices / VoronoiFace::compute_vertices read the geometry outputs
-        o.outputs |= ffi::TESS_OUT_VERTICES;
+        // the geometry outputs (vertex lists, face loops) are computed only for Cell::compute_vertices /
+        // VoronoiFace::compute_vertices: the first such call re-computes the batch with them
+        if vertices {
+            o.outputs |= ffi::TESS_OUT_VERTICES;
+        }
         o
     }
-    fn wrap(r: *mut ffi::tess_result) -> Rc<Batch> {
+    fn wrap(r: *mut ffi::tess_result, vertices: bool) -> Rc<Batch> {
         let mut b = Batch {
             r,
+            has_vertices: vertices,
             volumes: ptr::null(),
             face_offsets: ptr::null(),
             neighbors: ptr::null(),
@@ -161,29 +166,33 @@ impl<PointType: ToCeleryPoint<f64>> Diagram<PointType> {
             check(ffi::tess_result_face_offsets(r, &mut b.face_offsets));
             check(ffi::tess_result_neighbors(r, &mut b.neighbors));
             check(ffi::tess_result_areas(r, &mut b.areas));
-            check(ffi::tess_result_vertex_offsets(r, &mut b.vertex_offsets));
-            check(ffi::tess_result_vertices(r, &mut b.vertices));
-            check(ffi::tess_result_face_vertex_offsets(r, &mut b.face_vertex_offsets));
-            check(ffi::tess_result_face_vertex_indices(r, &mut b.face_vertex_indices));
+            if vertices {
+                check(ffi::tess_result_vertex_offsets(r, &mut b.vertex_offsets));
+                check(ffi::tess_result_vertices(r, &mut b.vertices));
+                check(ffi::tess_result_face_vertex_offsets(r, &mut b.face_vertex_offsets));
+                check(ffi::tess_result_face_vertex_indices(r, &mut b.face_vertex_indices));
+            }
         }
         Rc::new(b)
     }
-    fn batch(&self, search_radius: Option<f64>, target_group: Option<usize>) -> Rc<Batch> {
+    fn batch(&self, search_radius: Option<f64>, target_group: Option<usize>, vertices: bool) -> Rc<Batch> {
         let key = search_radius.map(|r| r.to_bits());
-        if let Some(hit) = self.batches.borrow().iter().find(|(r, g, _)| *r == key && *g == target_group) {
+        if let Some(hit) = self.batches.borrow().iter().find(|(r, g, b)| *r == key && *g == target_group && (b.has_vertices || !vertices)) {
             return hit.2.clone();
         }
-        let o = Self::opts(search_radius, target_group);
+        let o = Self::opts(search_radius, target_group, vertices);
         let mut r = ptr::null_mut();
         check(unsafe { ffi::tess_compute_all(self.d, &o, &mut r) });
-        let b = Self::wrap(r);
+        let b = Self::wrap(r, vertices);
+        // a batch with geometry replaces the one without (cells that hold the old one keep it alive)
+        self.batches.borrow_mut().retain(|(r, g, _)| !(*r == key && *g == target_group));
         self.batches.borrow_mut().push((key, target_group, b.clone()));
         b
     }
 
     /// Extension: every cell of the diagram in one batch (what the first `compute_voronoi_cell` triggers anyway).
     pub fn compute_all_cells(&self, search_radius: Option<f64>, target_group: Option<usize>) {
-        let _ = self.batch(search_radius, target_group);
+        let _ = self.batch(search_radius, target_group, false);
     }
     /// Number of particles added so far.
     pub fn len(&self) -> usize {
@@ -222,23 +231,37 @@ pub fn wall_neighbor(id: i64) -> usize {
 impl<'a, PointType: ToCeleryPoint<f64>> Cell<'a, PointType> {
     /// interface.rs:257-313
     pub fn compute_voronoi_cell(&mut self) {
+        self.compute(false);
+    }
+    fn compute(&mut self, vertices: bool) {
         match self.index {
             Some(i) => {
-                self.batch = Some(self.diagram.batch(self.search_radius, self.target_group));
+                self.batch = Some(self.diagram.batch(self.search_radius, self.target_group, vertices));
                 self.row = i;
             }
             None => {
-                let o = Diagram::<PointType>::opts(self.search_radius, self.target_group);
+                let o = Diagram::<PointType>::opts(self.search_radius, self.target_group, vertices);
                 let mut r = ptr::null_mut();
                 check(unsafe { ffi::tess_compute_at_points(self.diagram.d, &self.position as *const Vector3 as *const f64, 1, &o, &mut r) });
-                self.batch = Some(Diagram::<PointType>::wrap(r));
+                self.batch = Some(Diagram::<PointType>::wrap(r, vertices));
                 self.row = 0;
             }
         }
     }
     fn need(&mut self) -> Rc<Batch> {
         if self.batch.is_none() {
-            self.compute_voronoi_cell();
+            self.compute(false);
+        }
+        self.batch.as_ref().unwrap().clone()
+    }
+    /// the batch WITH the geometry outputs: computed on the first call that reads vertices
+    fn need_vertices(&mut self) -> Rc<Batch> {
+        let have = match self.batch.as_ref() {
+            Some(b) => b.has_vertices,
+            None => false,
+        };
+        if !have {
+            self.compute(true);
         }
         self.batch.as_ref().unwrap().clone()
     }
@@ -283,13 +306,14 @@ impl<'a, PointType: ToCeleryPoint<f64>> Cell<'a, PointType> {
     /// interface.rs:368-370: the vertices of the cell, in cell-local coordinates (relative to the particle, as the
     /// reference's polyhedron is translated by -position, interface.rs:266).
     pub fn compute_vertices(&mut self) -> Vec<Vector3> {
-        let b = self.need();
+        let b = self.need_vertices();
         let (lo, hi) = unsafe { (*b.vertex_offsets.add(self.row) as usize, *b.vertex_offsets.add(self.row + 1) as usize) };
         (lo..hi).map(|v| unsafe { Vector3 { x: *b.vertices.add(3 * v), y: *b.vertices.add(3 * v + 1), z: *b.vertices.add(3 * v + 2) } }).collect()
     }
-    /// interface.rs:373-384
+    /// interface.rs:373-384.  Faces carry the geometry batch (VoronoiFace::compute_vertices reads the loops): asking for
+    /// the faces is the request for geometry; volumes, neighbours and areas alone never compute it.
     pub fn compute_faces(&mut self) -> Vec<VoronoiFace> {
-        let b = self.need();
+        let b = self.need_vertices();
         let (lo, hi) = Self::range(&b, self.row);
         let row = self.row;
         (lo..hi).map(|k| VoronoiFace { batch: b.clone(), k, row }).collect()

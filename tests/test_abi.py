@@ -109,6 +109,49 @@ def test_rust_ffi_declares_only_functions_of_the_header():
     for name, args in r_decl.items():
         assert name in c_decl, f"{name} is not in tess.h"
         assert arity(args) == arity(c_decl[name]), f"{name}: {arity(args)} parameters in ffi.rs, {arity(c_decl[name])} in tess.h"
+
+    # parameter TYPES, one by one: the C type of tess.h translated to the Rust type it must be bound as
+    scalar = {"int": "c_int", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "size_t": "usize", "double": "f64", "char": "c_char", "void": "c_void",
+              "uint16_t": "u16", "tess_diagram": "tess_diagram", "tess_result": "tess_result", "tess_query": "tess_query", "tess_search": "tess_search",
+              "tess_opts": "tess_opts", "tess_slab": "tess_slab"}
+
+    def c_to_rust(decl: str) -> str:
+        decl = decl.strip()
+        decl = re.sub(r"\[[^\]]*\]\s*$", "*", re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*\s*(\[[^\]]*\])?\s*$", lambda m: m.group(1) or "", decl, count=1).strip())  # drop the name; T x[6] -> T*
+        toks = re.findall(r"const|\*|[A-Za-z_][A-Za-z0-9_]*", decl)
+        toks = [t for t in toks if t != "struct"]
+        base_const = toks[0] == "const"
+        if base_const:
+            toks = toks[1:]
+        base, stars = toks[0], [t for t in toks[1:] if t in ("*", "const")]
+        out = scalar[base]
+        # pointers from the inside out: the innermost one points at a (const?) base
+        const_next = base_const
+        i = 0
+        while i < len(stars):
+            assert stars[i] == "*", decl
+            out = ("*const " if const_next else "*mut ") + out
+            const_next = i + 1 < len(stars) and stars[i + 1] == "const"
+            i += 2 if const_next else 1
+        return out
+
+    def split_args(a: str):
+        a = a.strip()
+        return [] if a in ("", "void") else [x.strip() for x in a.split(",")]
+
+    checked = 0
+    for name, args in r_decl.items():
+        want = [c_to_rust(a) for a in split_args(c_decl[name])]
+        got = [re.sub(r"\s+", " ", a.split(":", 1)[1].strip()) for a in split_args(args)]
+        assert got == want, f"{name}: ffi.rs binds {got}, tess.h declares {want}"
+        checked += len(want)
+    assert checked > 90
+    # return types
+    c_ret = {m.group(2): m.group(1).strip() for m in re.finditer(r"^\s*([A-Za-z_][A-Za-z0-9_ \*]*?)\s*\b(tess_[a-z0-9_]+)\s*\(", hdr, flags=re.M)}
+    r_ret = {m.group(1): (m.group(2) or "").strip() for m in re.finditer(r"pub fn (tess_[a-z0-9_]+)\s*\(.*?\)\s*(?:->\s*([^;]+))?;", ffi, flags=re.S)}
+    for name in r_decl:
+        want = {"int": "c_int", "void": "", "uint64_t": "u64", "const char*": "*const c_char", "const char *": "*const c_char"}[c_ret[name]]
+        assert r_ret[name] == want, f"{name}: returns {r_ret[name]!r} in ffi.rs, {c_ret[name]!r} in tess.h"
     used = set(re.findall(r"ffi::(tess_[a-z0-9_]+)", open(os.path.join(root, "rust", "src", "interface.rs")).read()))
     types = set(re.findall(r"pub struct (tess_[a-z0-9_]+)", ffi))
     assert used - types <= set(r_decl), used - types - set(r_decl)

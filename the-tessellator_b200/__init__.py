@@ -9,6 +9,6 @@ The directory name contains a hyphen; import it with
 """
 from . import _lib, generators  # noqa: F401
 from ._lib import TessError, build  # noqa: F401
-from .interface import Cell, CellBatch, Diagram, Polyhedron, VoronoiFace, device_count, set_main_tier  # noqa: F401
+from .interface import Cell, CellBatch, Diagram, ExpandingSearch, Polyhedron, VoronoiFace, device_count, set_main_tier  # noqa: F401
 
-__all__ = ["Diagram", "Cell", "VoronoiFace", "Polyhedron", "CellBatch", "TessError", "build", "device_count", "set_main_tier", "generators"]
+__all__ = ["Diagram", "Cell", "VoronoiFace", "Polyhedron", "CellBatch", "ExpandingSearch", "TessError", "build", "device_count", "set_main_tier", "generators"]

@@ -32,7 +32,7 @@ SYMBOLS = (
     "tess_result_face_vertex_offsets", "tess_result_face_vertex_indices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
     "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs", "tess_pack_records", "tess_diagram_add_records_device",
-    "tess_find_neighbors", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
+    "tess_find_neighbors", "tess_find_cells_in_radius", "tess_search_create", "tess_search_expand", "tess_search_cursor", "tess_search_free", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
     "tess_result_download", "tess_set_main_tier", "tess_result_tier_stats", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
 
@@ -128,6 +128,11 @@ def lib() -> C.CDLL:
     sig("tess_result_device_views", ci, vp, P(vp), P(vp), P(vp), P(vp), P(vp), P(vp))
     sig("tess_result_download", ci, vp, vp, vp, vp, vp, vp, vp)
     sig("tess_find_neighbors", ci, vp, vp, sz, f64, ci, i64, vp, P(vp))
+    sig("tess_find_cells_in_radius", ci, vp, vp, sz, f64, vp, P(vp))
+    sig("tess_search_create", ci, vp, vp, sz, P(vp))
+    sig("tess_search_expand", ci, vp, f64, u64, vp, P(vp))
+    sig("tess_search_cursor", ci, vp, P(vp))
+    sig("tess_search_free", None, vp)
     sig("tess_query_free", None, vp)
     for n in ("tess_query_offsets", "tess_query_indices", "tess_query_status"):
         sig(n, ci, vp, P(vp))

@@ -1237,16 +1237,19 @@ struct tess_query {
     std::vector<uint32_t> status;
 };
 
+// ExpandingSearch (celery.rs:865-880) for m positions: the positions and each one's current_search_index
+struct tess_search {
+    const tess_diagram* d = nullptr;
+    std::vector<double> xyz;
+    std::vector<uint64_t> cursor;
+};
+
 extern "C" {
 
-int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, void* stream, tess_query** out) {
-    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
-    *out = nullptr;
-    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
-    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "radius queries need a whole-domain diagram");
-    if (mode < 0 || mode > 2) return fail(TESS_ERR_INVALID, "bad query mode");
-    TESS_TRY
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// One query pass pair (count, scan, fill) for m host positions.  mode 4 (ExpandingSearch::expand): cursors in / out (host, m
+// entries) and cells_to_add; the search table is widened until no walk runs off the end of a truncated one.
+static int run_query(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, const uint64_t* cursor_in,
+                     uint64_t* cursor_out, uint64_t cells_to_add, cudaStream_t s, tess_query** out) {
     TESS_CUDA_CHECK(cudaSetDevice(d->device));
     std::unique_ptr<tess_query> q(new tess_query());
     q->offsets.assign(m + 1, 0);
@@ -1261,8 +1264,10 @@ int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, doub
     uint32_t* flags = tmp.get<uint32_t>(m);
     uint64_t* offs = tmp.get<uint64_t>(m + 1);
     void* scan_tmp = tmp.get<char>(scan_tmp_bytes(m + 1));
+    uint64_t* cur_in = mode == 4 ? tmp.get<uint64_t>(m) : nullptr;
+    uint64_t* cur_out = mode == 4 ? tmp.get<uint64_t>(m) : nullptr;
     TESS_CUDA_CHECK(cudaMemcpyAsync(qx, xyz, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, s));
-    TESS_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (m + 1), s));
+    if (mode == 4) TESS_CUDA_CHECK(cudaMemcpyAsync(cur_in, cursor_in, sizeof(uint64_t) * m, cudaMemcpyHostToDevice, s));
     QueryParams Q{};
     Q.sorted = d->sorted.as<Particle>();
     Q.delim = d->delim.as<uint32_t>();
@@ -1275,24 +1280,39 @@ int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, doub
     Q.target_group = target_group;
     Q.counts = counts;
     Q.flags = flags;
-    if (mode == TESS_QUERY_NEIGHBOR_CLOUD) {
+    Q.cursor_in = cur_in;
+    Q.cursor_out = cur_out;
+    Q.cells_to_add = cells_to_add;
+    int R = 0;
+    if (mode == TESS_QUERY_NEIGHBOR_CLOUD || mode == 4) {
         // the table must hold every entry with key <= radius: (R*size)^2 > radius on every axis
         const double smin = std::min(d->grid.sx, std::min(d->grid.sy, d->grid.sz));
-        int R = static_cast<int>(d->grid.cpd);  // full table
+        R = static_cast<int>(d->grid.cpd);  // full table
         if (radius >= 0 && smin > 0) {
             const double need = std::sqrt(radius) / smin + 2.0;
             if (need < static_cast<double>(d->grid.cpd)) R = std::max(1, static_cast<int>(need));
         }
-        const ShellTable& t = d->table(R, s);
-        Q.table = t.dev.as<ShellEntry>();
-        Q.table_len = t.len;
-        Q.table_full = t.full ? 1u : 0u;
+        if (mode == 4) R = std::min(R, std::max(kDefaultTableRadius, 1));  // a few cells per call is the common use: start small, widen on demand
     }
-    launch_radius_query(Q, /*fill=*/false, s);
-    launch_exclusive_scan_u32_to_u64(counts, offs, m + 1, scan_tmp, scan_tmp_bytes(m + 1), s);
-    TESS_CUDA_CHECK(cudaMemcpyAsync(q->offsets.data(), offs, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, s));
-    TESS_CUDA_CHECK(cudaMemcpyAsync(q->status.data(), flags, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s));
-    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (;;) {
+        if (R > 0) {
+            const ShellTable& t = d->table(R, s);
+            Q.table = t.dev.as<ShellEntry>();
+            Q.table_len = t.len;
+            Q.table_full = t.full ? 1u : 0u;
+        }
+        TESS_CUDA_CHECK(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (m + 1), s));
+        launch_radius_query(Q, /*fill=*/false, s);
+        launch_exclusive_scan_u32_to_u64(counts, offs, m + 1, scan_tmp, scan_tmp_bytes(m + 1), s);
+        TESS_CUDA_CHECK(cudaMemcpyAsync(q->offsets.data(), offs, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaMemcpyAsync(q->status.data(), flags, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s));
+        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (mode != 4 || Q.table_full) break;
+        bool ran_off = false;
+        for (size_t i = 0; i < m; ++i) ran_off |= (q->status[i] & ST_TABLE_EXHAUSTED) != 0;
+        if (!ran_off) break;
+        R = std::min(2 * R, static_cast<int>(d->grid.cpd));
+    }
     const uint64_t total = q->offsets[m];
     q->indices.resize(total);
     if (total) {
@@ -1301,12 +1321,68 @@ int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, doub
         Q.indices = idx;
         launch_radius_query(Q, /*fill=*/true, s);
         TESS_CUDA_CHECK(cudaMemcpyAsync(q->indices.data(), idx, sizeof(int64_t) * total, cudaMemcpyDeviceToHost, s));
-        TESS_CUDA_CHECK(cudaStreamSynchronize(s));
     }
+    if (mode == 4) TESS_CUDA_CHECK(cudaMemcpyAsync(cursor_out, cur_out, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s));
+    TESS_CUDA_CHECK(cudaStreamSynchronize(s));
     *out = q.release();
+    return TESS_OK;
+}
+
+int tess_find_neighbors(const tess_diagram* d, const double* xyz, size_t m, double radius, int mode, int64_t target_group, void* stream, tess_query** out) {
+    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "radius queries need a whole-domain diagram");
+    if (mode < 0 || mode > 2) return fail(TESS_ERR_INVALID, "bad query mode");
+    TESS_TRY
+    return run_query(d, xyz, m, radius, mode, target_group, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream), out);
+    TESS_CATCH
+}
+
+int tess_find_cells_in_radius(const tess_diagram* d, const double* xyz, size_t m, double radius, void* stream, tess_query** out) {
+    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "radius queries need a whole-domain diagram");
+    TESS_TRY
+    return run_query(d, xyz, m, radius, 3, -1, nullptr, nullptr, 0, static_cast<cudaStream_t>(stream), out);
+    TESS_CATCH
+}
+
+int tess_search_create(const tess_diagram* d, const double* xyz, size_t m, tess_search** out) {
+    if (!d || !out || (!xyz && m)) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    if (d->slab) return fail(TESS_ERR_UNSUPPORTED, "radius queries need a whole-domain diagram");
+    TESS_TRY
+    std::unique_ptr<tess_search> sr(new tess_search());
+    sr->d = d;
+    sr->xyz.assign(xyz, xyz + 3 * m);
+    sr->cursor.assign(m, 0);  // current_search_index: 0 (celery.rs:895)
+    *out = sr.release();
     return TESS_OK;
     TESS_CATCH
 }
+
+int tess_search_expand(tess_search* sr, double max_radius, uint64_t cells_to_add, void* stream, tess_query** out) {
+    if (!sr || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (!sr->d->initialized) return fail(TESS_ERR_STATE, "diagram not initialized");
+    TESS_TRY
+    std::vector<uint64_t> next(sr->cursor.size());
+    const int rc = run_query(sr->d, sr->xyz.data(), sr->cursor.size(), max_radius, 4, -1, sr->cursor.data(), next.data(), cells_to_add, static_cast<cudaStream_t>(stream), out);
+    if (rc == TESS_OK && !sr->cursor.empty()) sr->cursor.swap(next);
+    return rc;
+    TESS_CATCH
+}
+
+int tess_search_cursor(const tess_search* sr, const uint64_t** out) {
+    if (!sr || !out) return fail(TESS_ERR_INVALID, "NULL argument");
+    *out = sr->cursor.data();
+    return TESS_OK;
+}
+
+void tess_search_free(tess_search* sr) { delete sr; }
 
 void tess_query_free(tess_query* q) { delete q; }
 int tess_query_offsets(tess_query* q, const uint64_t** out) {

@@ -104,7 +104,10 @@ struct QueryParams {
     const double* xyz;              // n_query positions (device)
     size_t n_query;
     double radius;
-    int mode;                       // 0 cell radius, 1 real radius, 2 expand_all_in_radius
+    int mode;                       // 0 cell radius, 1 real radius, 2 expand_all_in_radius, 3 find_cells_in_radius (grid cell ids), 4 ExpandingSearch::expand
+    const uint64_t* cursor_in;      // mode 4: current_search_index per query (celery.rs:873)
+    uint64_t* cursor_out;           // mode 4: ... after the call (written by the counting pass)
+    uint64_t cells_to_add;          // mode 4
     int64_t target_group;           // -1 = None
     uint32_t* counts;               // pass 1
     uint32_t* flags;

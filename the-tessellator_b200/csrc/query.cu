@@ -4,6 +4,8 @@
 //   mode 1  Celery::find_neighbors_in_real_radius   celery.rs:825-855
 //   mode 2  ExpandingSearch::expand_all_in_radius   celery.rs:1023-1075  (what Cell::compute_neighbor_cloud,
 //           interface.rs:348-365, calls; a target group filters the result, :359-362)
+//   mode 3  Celery::find_cells_in_radius            celery.rs:753-797    (grid cell ids instead of particles)
+//   mode 4  ExpandingSearch::expand                 celery.rs:907-963    (incremental: a cursor per query position)
 // all built on find_cells_in_radius (celery.rs:753-797) / check_cell_in_range (:708-743) and the
 // search-order table.  One warp answers one query; the kernel runs twice (count, then fill) around an
 // exclusive scan, and results come out in the reference's order: cells in i, j, k loop order (modes 0/1)
@@ -57,7 +59,40 @@ __global__ void __launch_bounds__(128) radius_query_kernel(const QueryParams P) 
         }
     };
 
-    if (P.mode == 2) {
+    // append one value (a grid cell id)
+    auto emit_value = [&](long long v) {
+        if (FILL && lane == 0) P.indices[out] = v;
+        out += 1;
+        count += 1;
+    };
+
+    if (P.mode == 4) {
+        // ExpandingSearch::expand (celery.rs:907-963): at most cells_to_add table entries from the cursor on — entries
+        // outside the grid count too (:937-946 `continue` after the cursor moved) — stopping BEFORE the first entry whose
+        // key exceeds max_radius (:925-928) and at the end of the table (:918-920)
+        const int cpd = (int)G.cpd;
+        const int hx = (int)axis_index(x, G.xmin, G.xmax, G.ix, G.cpd);
+        const int hy = (int)axis_index(y, G.ymin, G.ymax, G.iy, G.cpd);
+        const int hz = (int)axis_index(z, G.zmin, G.zmax, G.iz, G.cpd);
+        unsigned long long t = P.cursor_in[q];
+        bool ran_off = false;
+        for (unsigned long long it = 0; it < P.cells_to_add; ++it) {
+            if (t >= P.table_len) {
+                ran_off = !P.table_full;  // a truncated table: the caller widens it and asks again
+                break;
+            }
+            const ShellEntry e = P.table[t];
+            if (e.key > r) break;
+            ++t;
+            const int gx = hx + e.di, gy = hy + e.dj, gz = hz + e.dk;
+            if (gx < 0 || gx >= cpd || gy < 0 || gy >= cpd || gz < 0 || gz >= cpd) continue;
+            emit_cell(((uint32_t)gx * G.cpd + (uint32_t)gy) * G.cpd + (uint32_t)gz);
+        }
+        if (!FILL && lane == 0) {
+            P.cursor_out[q] = t;
+            P.flags[q] = ran_off ? ST_TABLE_EXHAUSTED : 0u;
+        }
+    } else if (P.mode == 2) {
         // expand_all_in_radius: walk the table until an entry's (squared) key exceeds max_radius (D11)
         const int cpd = (int)G.cpd;
         const int hx = (int)axis_index(x, G.xmin, G.xmax, G.ix, G.cpd);
@@ -94,7 +129,11 @@ __global__ void __launch_bounds__(128) radius_query_kernel(const QueryParams P) 
                     const int ox = max(0, abs(xi - (int)i) - 1), oy = max(0, abs(yi - (int)j) - 1), oz = max(0, abs(zi - (int)k) - 1);
                     const double tx = mul((double)ox, G.sx), ty = mul((double)oy, G.sy), tz = mul((double)oz, G.sz);
                     const double ds = addd(addd(mul(tx, tx), mul(ty, ty)), mul(tz, tz));
-                    if (ds <= rr) emit_cell((i * G.cpd + j) * G.cpd + k);
+                    if (ds <= rr) {
+                        const uint32_t c = (i * G.cpd + j) * G.cpd + k;  // get_cell_from_indices (celery.rs:317-325)
+                        if (P.mode == 3) emit_value((long long)c);
+                        else emit_cell(c);
+                    }
                 }
         if (!FILL && lane == 0) P.flags[q] = 0u;
     }

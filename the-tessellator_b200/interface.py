@@ -50,6 +50,7 @@ class CellBatch:
         check(_lib.lib().tess_result_n_cells(self._h, C.byref(nc), C.byref(nf)))
         self.n_cells, self.n_faces = int(nc.value), int(nf.value)
         self._cache = {}
+        self._has_vertices = False
 
     def close(self):
         if self._h:
@@ -371,17 +372,18 @@ class Diagram:
         p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         h = C.c_void_p(0)
         check(_lib.lib().tess_find_neighbors(self._h, p.ctypes.data, p.shape[0], float(radius), mode, -1 if target_group is None else int(target_group), stream or None, C.byref(h)))
-        try:
-            po, pi = C.c_void_p(0), C.c_void_p(0)
-            check(_lib.lib().tess_query_offsets(h, C.byref(po)))
-            check(_lib.lib().tess_query_indices(h, C.byref(pi)))
-            m = p.shape[0]
-            off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(m + 1,)).astype(np.int64)
-            tot = int(off[-1])
-            idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int64)), shape=(tot,)).copy() if tot else np.zeros(0, np.int64)
-            return [idx[off[i]:off[i + 1]] for i in range(m)]
-        finally:
-            _lib.lib().tess_query_free(h)
+        return _query_lists(h, p.shape[0])
+
+    def find_cells_in_radius(self, x: float, y: float, z: float, radius: float, stream: int = 0) -> list:
+        """Celery::find_cells_in_radius (celery.rs:753-797): ids of the grid cells within `radius` of the position."""
+        p = np.array([[x, y, z]], dtype=np.float64)
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_find_cells_in_radius(self._h, p.ctypes.data, 1, float(radius), stream or None, C.byref(h)))
+        return _query_lists(h, 1)[0].tolist()
+
+    def expanding_search(self, points) -> "ExpandingSearch":
+        """ExpandingSearch::new (celery.rs:882-902) around one position (x, y, z) or around m positions at once."""
+        return ExpandingSearch(self, points)
 
     def find_neighbors_in_cell_radius(self, x: float, y: float, z: float, radius: float) -> list:
         """Celery::find_neighbors_in_cell_radius (celery.rs:802-819)."""
@@ -395,10 +397,16 @@ class Diagram:
         if not np.array_equal(polyhedron.as_box(), self._box):
             raise _lib.TessError(-5, "the start polyhedron of a cell must be the diagram's container box")
 
-    def _batch(self, search_radius, target_group) -> CellBatch:
+    def _batch(self, search_radius, target_group, vertices: bool = False) -> CellBatch:
+        """All cells for one (search_radius, target_group), computed once; the geometry outputs (vertex lists, face loops) only
+        when a caller asks for vertices (Cell.compute_vertices / VoronoiFace.compute_vertices)."""
         key = (None if search_radius is None else float(search_radius), target_group)
-        if key not in self._batches:
-            self._batches[key] = self.compute_all_cells(search_radius, target_group, outputs=_lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | _lib.OUT_VERTICES)
+        have = self._batches.get(key)
+        if have is None or (vertices and not have._has_vertices):
+            out = _lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | (_lib.OUT_VERTICES if vertices else 0)
+            new = self.compute_all_cells(search_radius, target_group, outputs=out)
+            new._has_vertices = vertices
+            self._batches[key] = new  # (cells that hold the earlier batch keep it alive; it is freed with them)
         return self._batches[key]
 
     def get_cell_at_index(self, index: int, polyhedron: Polyhedron, search_radius: Optional[float] = None, target_group: Optional[int] = None) -> "Cell":
@@ -423,19 +431,20 @@ class Cell:
         self._batch: Optional[CellBatch] = None
         self._row = 0
 
-    def compute_voronoi_cell(self) -> None:
+    def compute_voronoi_cell(self, vertices: bool = False) -> None:
         """interface.rs:257-313."""
         if self.index is not None:
-            self._batch, self._row = self.diagram._batch(self.search_radius, self.target_group), self.index
+            self._batch, self._row = self.diagram._batch(self.search_radius, self.target_group, vertices), self.index
         else:
             self._batch = self.diagram.compute_cells_at(
                 np.array([self.position]), self.search_radius, self.target_group,
-                outputs=_lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | _lib.OUT_VERTICES)
+                outputs=_lib.OUT_VOLUME | _lib.OUT_NEIGHBORS | _lib.OUT_AREAS | (_lib.OUT_VERTICES if vertices else 0))
+            self._batch._has_vertices = vertices
             self._row = 0
 
-    def _need(self) -> CellBatch:
-        if self._batch is None:
-            self.compute_voronoi_cell()
+    def _need(self, vertices: bool = False) -> CellBatch:
+        if self._batch is None or (vertices and not getattr(self._batch, "_has_vertices", False)):
+            self.compute_voronoi_cell(vertices)
             # a cell no tier could finish (more than 1024 vertices / 512 faces, an inconsistent mesh, a search table the
             # redo passes could not widen enough) has no geometry to hand out: say so instead of returning volume 0
             st = int(self._batch.status[self._row])
@@ -456,7 +465,7 @@ class Cell:
 
     def compute_vertices(self) -> np.ndarray:
         """interface.rs:368-370: vertices in cell-local coordinates (relative to the particle)."""
-        return self._need().cell_vertices(self._row).copy()
+        return self._need(vertices=True).cell_vertices(self._row).copy()
 
     def compute_faces(self) -> list:
         """interface.rs:373-384."""
@@ -493,7 +502,67 @@ class VoronoiFace:
 
     def compute_vertices(self) -> np.ndarray:
         """interface.rs:403-405: the face's vertices in loop order, cell-local coordinates."""
-        return self.cell._batch.face_vertices(self.cell._row, self._k).copy()
+        return self.cell._need(vertices=True).face_vertices(self.cell._row, self._k).copy()
+
+
+def _query_lists(h, m: int) -> list:
+    """CSR result of a query call -> one index array per position; frees the handle."""
+    try:
+        po, pi = C.c_void_p(0), C.c_void_p(0)
+        check(_lib.lib().tess_query_offsets(h, C.byref(po)))
+        check(_lib.lib().tess_query_indices(h, C.byref(pi)))
+        off = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_uint64)), shape=(m + 1,)).astype(np.int64) if m else np.zeros(1, np.int64)
+        tot = int(off[-1])
+        idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_int64)), shape=(tot,)).copy() if tot else np.zeros(0, np.int64)
+        return [idx[off[i]:off[i + 1]] for i in range(m)]
+    finally:
+        _lib.lib().tess_query_free(h)
+
+
+class ExpandingSearch:
+    """celery.rs:865 `ExpandingSearch`: an outward walk over the grid cells around a position, resumable.  Built for one
+    position it returns plain lists like the reference; built for m positions every call returns one list per position."""
+
+    def __init__(self, diagram: Diagram, points):
+        p = np.ascontiguousarray(points, dtype=np.float64)
+        self._single = p.ndim == 1
+        self._p = p.reshape(-1, 3)
+        self._d = diagram
+        self._h = C.c_void_p(0)
+        check(_lib.lib().tess_search_create(diagram._h, self._p.ctypes.data, self._p.shape[0], C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.lib().tess_search_free(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def expand(self, max_radius: float, cells_to_add: int, stream: int = 0):
+        """celery.rs:907-963."""
+        h = C.c_void_p(0)
+        check(_lib.lib().tess_search_expand(self._h, float(max_radius), min(int(cells_to_add), 2 ** 64 - 1), stream or None, C.byref(h)))
+        out = _query_lists(h, self._p.shape[0])
+        return out[0].tolist() if self._single else out
+
+    def expand_all_in_radius(self, max_radius: float):
+        """celery.rs:1023-1075 (on a search that has not moved yet)."""
+        return self.expand(max_radius, 2 ** 64 - 1)
+
+    def expand_all_no_radius(self):
+        """celery.rs:971-1018."""
+        return self.expand(float("inf"), 2 ** 64 - 1)
+
+    @property
+    def current_search_index(self):
+        pc = C.c_void_p(0)
+        check(_lib.lib().tess_search_cursor(self._h, C.byref(pc)))
+        cur = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint64)), shape=(self._p.shape[0],)).copy()
+        return int(cur[0]) if self._single else cur
 
 
 MAIN_TIERS = {0: "small", 3: "fast", 4: "thread"}
