@@ -128,8 +128,11 @@ struct SmemMask {
 // ---------------------------------------------------------------------------------------------
 // Configurations
 // ---------------------------------------------------------------------------------------------
+#ifndef TESS_SMALL_WARPS
+#define TESS_SMALL_WARPS 1    // warps per CTA of the small configuration (A/B on 1M uniform at 32 warps per SM: 4 -> 18.94 ms, 2 -> 19.20, 1 -> 17.98)
+#endif
 #ifndef TESS_CLIP_MINBLOCKS
-#define TESS_CLIP_MINBLOCKS 8  // resident CTAs per SM the small kernel is compiled for (64 registers; A/B on 1M uniform: 5 -> 20.75 ms, 6 -> 20.05, 7 -> 19.17, 8 -> 18.59, 9 -> 18.94, 10 -> 20.06)
+#define TESS_CLIP_MINBLOCKS (32 / TESS_SMALL_WARPS)  // resident CTAs per SM the small kernel is compiled for: 32 warps per SM, 64 registers (A/B on 1M uniform with 4-warp CTAs: 20 warps -> 20.75 ms, 24 -> 20.05, 28 -> 19.17, 32 -> 18.59, 36 -> 18.94, 40 -> 20.06)
 #endif
 // A staged tile with at least this many candidates waiting is screened candidate-parallel before the planes
 // are offered one by one (0 disables the screen); see the comment at its use.
@@ -140,7 +143,7 @@ struct SmallCfg {
     static constexpr int MINB = TESS_CLIP_MINBLOCKS;
     static constexpr int VMAX = 64, EMAX = 256, FMAX = 64;
     static constexpr int E_LIMIT = 255;  // slot 255 is the "none" marker of 8-bit ids
-    static constexpr int WARPS = 4;
+    static constexpr int WARPS = TESS_SMALL_WARPS;
     static constexpr bool REG = true;
     using Idx = uint8_t;
     using EdgeWord = uint32_t;
@@ -612,6 +615,7 @@ __device__ int cut_parallel(Mesh<Cfg>& M, const Plane& pl, long long neighbor_id
         const int from_stack = pops < M.e_top ? pops : M.e_top;
         M.e_hwm += pops - from_stack;
         M.e_top -= from_stack;
+        __syncwarp();  // every lane has read its slots off the stack (pop_slot) before lane 0 puts one back (racecheck: WAR)
         if (lane == 0) {
             sm->estack[M.e_top] = (Idx)red;
             sm->edge[red] = MeshT::FREE_EDGE;
@@ -1029,8 +1033,10 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
 #else
     extern __shared__ __align__(16) unsigned char smem_raw[];
 #endif
-    WarpSmem<Cfg>* sm = reinterpret_cast<WarpSmem<Cfg>*>(smem_raw) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    // one warp per CTA (small and large configurations): the tables sit at the CTA's shared-memory base, a constant —
+    // no pointer to keep in registers or to re-derive from the thread index
+    WarpSmem<Cfg>* sm = reinterpret_cast<WarpSmem<Cfg>*>(smem_raw) + (Cfg::WARPS == 1 ? 0u : (threadIdx.x >> 5));
+    const int lane = Cfg::WARPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
     MeshT M;
     M.bind(sm, lane);
 
