@@ -345,6 +345,31 @@ def main():
         dist.all_reduce(vsum)
         dist.all_reduce(ncell)
     closure = abs(float(vsum.item()) - 1.0)
+    # parity properties that hold at any size (the oracle comparison at size is tests/test_gpu_parity.py: configs 2-5):
+    # no cell left flagged; for the BCC workload the analytic cell (truncated octahedron: 14 faces, V = a^3/2; the 1e-3 a
+    # jitter moves volumes by < 2e-2 relative) on every interior cell
+    hb0 = state["batch"]
+    st_bad = int(np.count_nonzero(hb0.status))
+    extra = torch.tensor([st_bad, 0, 0], dtype=torch.int64, device=dev)
+    vdev = torch.zeros(1, dtype=torch.float64, device=dev)
+    if kind == "bcc":
+        m = round((n / 2) ** (1 / 3))
+        ids = hb0.cell_ids.astype(np.int64)
+        site = ids // 2
+        ii, jj, kk = site // (m * m), (site // m) % m, site % m
+        inner = (np.minimum(np.minimum(ii, jj), kk) >= 2) & (np.maximum(np.maximum(ii, jj), kk) <= m - 3)
+        nfc = np.diff(hb0.face_offsets.astype(np.int64))
+        a3 = (1.0 / m) ** 3 / 2
+        extra[1] = int(np.count_nonzero(inner))
+        extra[2] = int(np.count_nonzero(nfc[inner] == 14))
+        vdev[0] = float(np.max(np.abs(hb0.volumes[inner] - a3) / a3)) if inner.any() else 0.0
+    if world > 1:
+        dist.all_reduce(extra)
+        dist.all_reduce(vdev, op=dist.ReduceOp.MAX)
+    size_checks = {"cells_with_status_flags": int(extra[0].item())}
+    if kind == "bcc":
+        size_checks.update({"bcc_interior_cells": int(extra[1].item()), "bcc_interior_cells_with_14_faces": int(extra[2].item()),
+                            "bcc_max_rel_volume_deviation_from_a3_over_2": float(vdev.item())})
 
     # ---- e2e: host buffers in, host buffers out ---------------------------------------------------
     e2e = None
@@ -473,8 +498,8 @@ def main():
         "config": workload_config(args, n, kind, seed, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / max(1, args.steps),
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_fp64": roofline_fp64, "roofline_binning": roofline_binning, "cpu_baseline": cpu_baseline,
-        "checks": {"cells": int(ncell[0].item()), "faces": int(ncell[1].item()), "abs_volume_closure_error": closure, "wall_ms_per_step": wall_ms / args.steps,
-                   "outputs_ms": float(np.mean(out_ms))},
+        "checks": dict({"cells": int(ncell[0].item()), "faces": int(ncell[1].item()), "abs_volume_closure_error": closure, "wall_ms_per_step": wall_ms / args.steps,
+                        "outputs_ms": float(np.mean(out_ms))}, **size_checks),
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
