@@ -39,6 +39,18 @@ pub struct tess_opts {
     pub stream: *mut c_void,
 }
 
+/// One rank's part of a slab-sharded diagram (tess.h `tess_slab`).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct tess_slab {
+    pub bounds: [f64; 6],
+    pub n_global: u64,
+    pub own_lo: u32,
+    pub own_hi: u32,
+    pub local_lo: u32,
+    pub local_hi: u32,
+}
+
 extern "C" {
     pub fn tess_last_error() -> *const c_char;
     pub fn tess_opts_default(o: *mut tess_opts);
@@ -78,6 +90,18 @@ extern "C" {
     pub fn tess_search_expand(s: *mut tess_search, max_radius: f64, cells_to_add: u64, stream: *mut c_void, out: *mut *mut tess_query) -> c_int;
     pub fn tess_search_cursor(s: *const tess_search, current_search_index: *mut *const u64) -> c_int;
     pub fn tess_search_free(s: *mut tess_search);
+    // slab partition (one process per GPU; the two collectives — all-reduce and all-to-all — are the host application's)
+    pub fn tess_bounds(xyz_dev: *const f64, n: usize, bounds_dev: *mut f64, stream: *mut c_void) -> c_int;
+    pub fn tess_plane_histogram(xyz_dev: *const f64, n: usize, bounds: *const f64, n_global: u64, counts_dev: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn tess_pack_records(xyz_dev: *const f64, ids_dev: *const i64, id_base: i64, n: usize, bounds: *const f64, n_global: u64, n_ranks: c_int, plane_lo: *const u32,
+                             plane_hi: *const u32, planned_counts: *const u64, counts_host: *mut u64, counts_dev: *mut u64, out_rec_dev: *mut f64, cap: usize,
+                             stream: *mut c_void) -> c_int;
+    pub fn tess_diagram_add_records_device(d: *mut tess_diagram, rec_dev: *const f64, n: usize, stream: *mut c_void) -> c_int;
+    pub fn tess_diagram_add_particles_device(d: *mut tess_diagram, xyz_dev: *const f64, n: usize, groups_dev: *const u64, ids_dev: *const i64, stream: *mut c_void) -> c_int;
+    pub fn tess_diagram_initialize_slab(d: *mut tess_diagram, box6: *const f64, slab: *const tess_slab, stream: *mut c_void) -> c_int;
+    pub fn tess_result_download(r: *const tess_result, volumes: *mut f64, face_offsets: *mut u64, neighbors: *mut i64, areas: *mut f64, status: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn tess_result_device_views(r: *const tess_result, volumes: *mut *const f64, face_offsets: *mut *const u64, neighbors: *mut *const i64, areas: *mut *const f64,
+                                    status: *mut *const u32, cell_ids: *mut *const i64) -> c_int;
     pub fn tess_query_free(q: *mut tess_query);
     pub fn tess_query_offsets(q: *mut tess_query, out: *mut *const u64) -> c_int;
     pub fn tess_query_indices(q: *mut tess_query, out: *mut *const i64) -> c_int;

@@ -155,3 +155,23 @@ def test_rust_ffi_declares_only_functions_of_the_header():
     used = set(re.findall(r"ffi::(tess_[a-z0-9_]+)", open(os.path.join(root, "rust", "src", "interface.rs")).read()))
     types = set(re.findall(r"pub struct (tess_[a-z0-9_]+)", ffi))
     assert used - types <= set(r_decl), used - types - set(r_decl)
+
+
+def test_rust_repr_c_structs_match_the_header():
+    """tess_opts and tess_slab cross the boundary by value/pointer: field order, names and types must match tess.h."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "tess.h")).read(), flags=re.S)
+    ffi = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
+    ctype = {"double": "f64", "int64_t": "i64", "uint64_t": "u64", "uint32_t": "u32", "int32_t": "i32", "void*": "*mut c_void"}
+    for name in ("tess_opts", "tess_slab"):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+        c_fields = []
+        for decl in [d.strip() for d in body.split(";") if d.strip()]:
+            m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)(\[(\d+)\])?$", decl)
+            t = ctype[m.group(1).replace(" ", "")]
+            c_fields.append((m.group(2), "[%s; %s]" % (t, m.group(4)) if m.group(4) else t))
+        rbody = re.search(r"#\[repr\(C\)\]\s*(?:#\[derive\([^)]*\)\]\s*)?pub struct %s \{(.*?)\}" % name, ffi, flags=re.S).group(1)
+        r_fields = [(m.group(1), m.group(2).strip()) for m in re.finditer(r"pub ([a-z_0-9]+): ([^,]+),", rbody)]
+        assert r_fields == c_fields, (name, r_fields, c_fields)
