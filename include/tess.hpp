@@ -311,4 +311,54 @@ inline Cell Diagram::get_cell_at_particle(const Vector3& point, const Polyhedron
     return Cell(this, std::nullopt, point, search_radius, target_group);
 }
 
+/// celery.rs:865 `ExpandingSearch`: an outward walk over the grid cells around a position, resumable
+/// (tess_search_create / tess_search_expand of tess.h).
+class ExpandingSearch {
+   public:
+    /// ExpandingSearch::new (celery.rs:882-902)
+    ExpandingSearch(const Diagram& d, const Vector3& position) { check(tess_search_create(d.handle(), reinterpret_cast<const double*>(&position), 1, &s_)); }
+    ~ExpandingSearch() { tess_search_free(s_); }
+    ExpandingSearch(const ExpandingSearch&) = delete;
+    ExpandingSearch& operator=(const ExpandingSearch&) = delete;
+    /// celery.rs:907-963: the particles of at most cells_to_add further grid cells, none beyond max_radius (squared cell distance)
+    std::vector<size_t> expand(double max_radius, uint64_t cells_to_add) {
+        tess_query* q = nullptr;
+        check(tess_search_expand(s_, max_radius, cells_to_add, nullptr, &q));
+        const uint64_t* off = nullptr;
+        const int64_t* idx = nullptr;
+        std::vector<size_t> out;
+        const int rc1 = tess_query_offsets(q, &off), rc2 = tess_query_indices(q, &idx);
+        if (rc1 == TESS_OK && rc2 == TESS_OK) out.assign(idx + off[0], idx + off[1]);
+        tess_query_free(q);
+        check(rc1);
+        check(rc2);
+        return out;
+    }
+    std::vector<size_t> expand_all_in_radius(double max_radius) { return expand(max_radius, UINT64_MAX); }                      // celery.rs:1023-1075
+    std::vector<size_t> expand_all_no_radius() { return expand(std::numeric_limits<double>::infinity(), UINT64_MAX); }  // celery.rs:971-1018
+    uint64_t current_search_index() const {
+        const uint64_t* c = nullptr;
+        check(tess_search_cursor(s_, &c));
+        return c[0];
+    }
+
+   private:
+    tess_search* s_ = nullptr;
+};
+
+/// Celery::find_cells_in_radius (celery.rs:753-797): ids of the grid cells within `radius` of the position
+inline std::vector<size_t> find_cells_in_radius(const Diagram& d, const Vector3& position, double radius) {
+    tess_query* q = nullptr;
+    check(tess_find_cells_in_radius(d.handle(), reinterpret_cast<const double*>(&position), 1, radius, nullptr, &q));
+    const uint64_t* off = nullptr;
+    const int64_t* idx = nullptr;
+    std::vector<size_t> out;
+    const int rc1 = tess_query_offsets(q, &off), rc2 = tess_query_indices(q, &idx);
+    if (rc1 == TESS_OK && rc2 == TESS_OK) out.assign(idx + off[0], idx + off[1]);
+    tess_query_free(q);
+    check(rc1);
+    check(rc2);
+    return out;
+}
+
 }  // namespace tess

@@ -56,6 +56,18 @@ int main(int argc, char** argv) {
         // a cell around a point that is not a particle (interface.rs:211-232)
         tess::Cell q = diagram.get_cell_at_particle(tess::Vector3{0.31, 0.62, 0.44}, box);
         std::printf("query volume %.17g nfaces %zu\n", q.compute_volume(), q.compute_neighbors().size());
+        // ExpandingSearch in steps (celery.rs:907-963) must visit what one sweep visits, in the same order
+        {
+            tess::ExpandingSearch a(diagram, tess::Vector3{0.31, 0.62, 0.44}), b(diagram, tess::Vector3{0.31, 0.62, 0.44});
+            std::vector<size_t> steps;
+            for (int i = 0; i < 40; ++i) {
+                const auto part = a.expand(0.01, 5);
+                steps.insert(steps.end(), part.begin(), part.end());
+            }
+            const auto all = b.expand(0.01, 200);
+            std::printf("expand steps %zu sweep %zu equal %d cursor %llu cells_in_radius %zu\n", steps.size(), all.size(), (int)(steps == all),
+                        (unsigned long long)a.current_search_index(), tess::find_cells_in_radius(diagram, tess::Vector3{0.31, 0.62, 0.44}, 0.1).size());
+        }
         // the batch call that streams into host arrays must agree with the per-cell interface
         {
             std::vector<double> vol(n), area(64 * n);

@@ -38,3 +38,8 @@ def test_cpp_harness_matches_oracle(tess, gen, ob, tmp_path):
     mq = re.search(r"query volume (\S+) nfaces (\d+)", out)
     assert abs(float(mq.group(1)) - q.volumes[0]) <= 1e-12 * q.volumes[0] and int(mq.group(2)) == len(q.neighbors)
     assert "expected error -5" in out
+    me = re.search(r"expand steps (\d+) sweep (\d+) equal (\d) cursor (\d+) cells_in_radius (\d+)", out)
+    es = od.expanding_search(0.31, 0.62, 0.44)
+    want = es.expand(0.01, 200)
+    assert int(me.group(3)) == 1 and int(me.group(1)) == int(me.group(2)) == len(want) > 0
+    assert int(me.group(5)) == len(od.find_cells_in_radius(0.31, 0.62, 0.44, 0.1))

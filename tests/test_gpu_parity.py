@@ -472,6 +472,61 @@ def test_slab_decomposition_is_bit_identical(tess, gen):
     whole.close()
 
 
+def test_record_exchange_path_on_one_device(tess, gen):
+    """The multi-GPU step's own kernels on one device: tess_pack_records routes one rank's particles to three fake ranks
+    as 32-byte records (with and without planned counts), each segment goes through tess_diagram_add_records_device +
+    initialize_slab + compute, and every cell equals the whole-domain run bit for bit.  A plan that does not fit the
+    particles is detected through the packed counts and never writes past a planned segment."""
+    import importlib
+
+    import torch
+
+    D = importlib.import_module("the-tessellator_b200.distributed")
+    pts = gen.uniform(80_000, 66)
+    n = len(pts)
+    whole = _diagram(tess, pts)
+    wb = whole.compute_all_cells()
+    be = D.CudaSlabBackend(0)
+    xyz = torch.from_numpy(pts).cuda()
+    b6 = be.bounds(xyz).cpu().numpy()
+    cpd = D.cells_per_dimension(n)
+    cuts = D.slab_cuts(be.plane_histogram(xyz, b6, n).cpu().numpy(), 3)
+    lo, hi = D.receive_ranges(cuts, 4)
+    counts, rec, counts_dev = be.pack_records(xyz, 0, b6, n, lo, hi)
+    assert counts == [int(v) for v in counts_dev.cpu().tolist()] and sum(counts) == rec.shape[0] > n
+    rec = rec.clone()
+    # the same with the counts as a plan: no counting pass, same multiset of records per segment
+    counts2, rec2, counts_dev2 = be.pack_records(xyz, 0, b6, n, lo, hi, planned_counts=counts)
+    assert counts2 == counts and [int(v) for v in counts_dev2.cpu().tolist()] == counts
+    o = 0
+    seen = np.zeros(n, bool)
+    for g in range(3):
+        seg, seg2 = rec[o:o + counts[g]], rec2[o:o + counts[g]]
+        ids1 = np.sort(seg[:, 3].contiguous().view(torch.int64).cpu().numpy())
+        assert np.array_equal(ids1, np.sort(seg2[:, 3].contiguous().view(torch.int64).cpu().numpy()))
+        batch, n_owned, flag = be.compute_records(seg.contiguous(), BOX, b6, n, (cuts[g], cuts[g + 1]), (lo[g], hi[g]), dict(outputs=7))
+        assert int(flag.item()) == 0 and n_owned == batch.n_cells
+        ids = batch.cell_ids
+        seen[ids] = True
+        assert np.array_equal(batch.volumes, wb.volumes[ids])
+        wfo = wb.face_offsets
+        for k in range(0, len(ids), 499):
+            i = ids[k]
+            assert np.array_equal(batch.cell_neighbors(k), wb.neighbors[wfo[i]:wfo[i + 1]]) and np.array_equal(batch.cell_areas(k), wb.areas[wfo[i]:wfo[i + 1]])
+        o += counts[g]
+    assert seen.all()
+    # a stale plan (counts of another particle set, some too small): detected, nothing written past the segments
+    other = torch.from_numpy(gen.uniform(n, 67)).cuda()
+    small = [c - 50 for c in counts]
+    c3, rec3, dev3 = be.pack_records(other, 0, b6, n, lo, hi, planned_counts=small)
+    assert c3 == small and [int(v) for v in dev3.cpu().tolist()] != small and rec3.shape[0] == sum(small)
+    # and the whole pipeline as one rank (no process group): plan, then the planned step
+    res = D.compute_sharded(be, xyz, 0, n, BOX)
+    res2 = D.compute_sharded(be, xyz, 0, n, BOX, plan=res.plan)
+    assert res2.rounds == 1 and np.array_equal(res2.batch.volumes, wb.volumes[res2.batch.cell_ids])
+    whole.close()
+
+
 # ------------------------------------------------------------------ full-size configs --------
 def _full_size_checks(tess, gen, ob, pts, sample_seed, n_sample, box=BOX):
     d = _diagram(tess, pts, box)

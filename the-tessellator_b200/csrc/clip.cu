@@ -1255,7 +1255,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                     stop_thr = mul(4.0, M.max_radius_sq());
                     stale_thr = false;
                 }
-                c_vis += __popc(uncounted & __ballot_sync(FULL, !(src_key > stop_thr)));
+                if (COUNT) c_vis += __popc(uncounted & __ballot_sync(FULL, !(src_key > stop_thr)));
                 // the walk stops at the first entry whose key exceeds the threshold (celery.rs:1036)
                 if (__ballot_sync(FULL, has && src_key > stop_thr)) done = true;
             }
@@ -1263,15 +1263,15 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 const uint32_t stopm = __ballot_sync(FULL, tvalid && key > stop_thr);
                 if (stopm) {
                     done = true;
-                    c_tab += __ffs(stopm) - 1;
-                } else {
+                    if (COUNT) c_tab += __ffs(stopm) - 1;
+                } else if (COUNT) {
                     c_tab += __popc(__ballot_sync(FULL, tvalid));
                 }
                 if (!done && t0 + 32 >= P.table_len) {
                     if (!P.table_full) status |= ST_TABLE_EXHAUSTED;  // (both modes: a table that ends before a key exceeds the threshold has to be widened)
                     done = true;
                 }
-            } else if (!failed) {
+            } else if (COUNT && !failed) {
                 c_tab += __popc(__ballot_sync(FULL, tvalid && !(key > stop_thr)));
             }
         }
