@@ -745,6 +745,7 @@ __device__ int cut_with_plane(Mesh<Cfg>& M, const Plane& pl, long long neighbor_
     //      and every later vector_location call of the walk) --------------------------------------
     uint32_t any_out = 0, any_incident = 0;
     uint32_t nlive = 0, n_out = 0;
+    if constexpr (Cfg::REG) __syncwarp();  // the previous plane's readers of ovl[] are done (racecheck: the full-mask votes order execution, not memory)
 #pragma unroll
     for (int p = 0; p < MeshT::NWV; ++p) {
         if (p >= M.nwv()) break;
@@ -1154,6 +1155,7 @@ __global__ void __launch_bounds__(Cfg::WARPS * 32, Cfg::MINB) clip_kernel(const 
                 uint32_t uncounted = __ballot_sync(FULL, has && !src_marker);  // C_vis bookkeeping
                 // bisector plane of every candidate that can still matter (Plane::halfway_from_origin_to)
                 const bool cand = (has && src_marker) || (adm && rej_ok(r2));
+                __syncwarp();  // the previous tile's planes have all been read
                 if (cand && !src_marker) {
                     const Plane mypl = halfway_from_origin_to(Vec3{rx, ry, rz});
                     sm->cand_plane[lane] = make_double4(mypl.nx, mypl.ny, mypl.nz, mypl.off);
