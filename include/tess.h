@@ -87,6 +87,9 @@ typedef struct tess_slab {
     uint32_t own_hi;
     uint32_t local_lo;   /* x-planes [local_lo, local_hi) held by this rank (owned + halo) */
     uint32_t local_hi;
+    uint32_t own_lo_row; /* finer ownership: the owned cells are the grid rows (x, y) with own_lo*cpd + own_lo_row <= x*cpd + y <  */
+    uint32_t own_hi_row; /* own_hi*cpd + own_hi_row (cell ids are x-major, celery.rs:323-324: a contiguous run of the sorted order). */
+                         /* 0, 0 = whole planes.  A partly owned plane own_hi must be held locally (own_hi < local_hi).                */
 } tess_slab;
 
 const char* tess_last_error(void);
@@ -224,6 +227,9 @@ int tess_query_status(tess_query* q, const uint32_t** out);   /* m; TESS_STATUS_
 
 /* Histogram of particles per global grid x-plane: counts_dev[cpd] (u64, device, zeroed by the call). */
 int tess_plane_histogram(const double* xyz_dev, size_t n, const double bounds[6], uint64_t n_global, uint64_t* counts_dev, void* stream);
+/* The same per grid row (x, y): counts_dev[cpd*cpd] (u64, device, zeroed by the call), index x*cpd + y — for slab cuts finer
+ * than a plane (tess_slab.own_lo_row / own_hi_row). */
+int tess_row_histogram(const double* xyz_dev, size_t n, const double bounds[6], uint64_t n_global, uint64_t* counts_dev, void* stream);
 /* min/max of packed xyz on the device -> bounds_dev[6] (x_min,x_max,y_min,y_max,z_min,z_max). */
 int tess_bounds(const double* xyz_dev, size_t n, double* bounds_dev, void* stream);
 /* Route particles to slabs.  plane_lo/plane_hi[g] (host, n_ranks entries) give for destination

@@ -49,6 +49,8 @@ pub struct tess_slab {
     pub own_hi: u32,
     pub local_lo: u32,
     pub local_hi: u32,
+    pub own_lo_row: u32,
+    pub own_hi_row: u32,
 }
 
 extern "C" {
@@ -93,6 +95,7 @@ extern "C" {
     // slab partition (one process per GPU; the two collectives — all-reduce and all-to-all — are the host application's)
     pub fn tess_bounds(xyz_dev: *const f64, n: usize, bounds_dev: *mut f64, stream: *mut c_void) -> c_int;
     pub fn tess_plane_histogram(xyz_dev: *const f64, n: usize, bounds: *const f64, n_global: u64, counts_dev: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn tess_row_histogram(xyz_dev: *const f64, n: usize, bounds: *const f64, n_global: u64, counts_dev: *mut u64, stream: *mut c_void) -> c_int;
     pub fn tess_pack_records(xyz_dev: *const f64, ids_dev: *const i64, id_base: i64, n: usize, bounds: *const f64, n_global: u64, n_ranks: c_int, plane_lo: *const u32,
                              plane_hi: *const u32, planned_counts: *const u64, counts_host: *mut u64, counts_dev: *mut u64, out_rec_dev: *mut f64, cap: usize,
                              stream: *mut c_void) -> c_int;

@@ -33,7 +33,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False):
+def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False, rows=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -70,7 +70,26 @@ def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False):
                 pi.append(ids[m])
             return counts, torch.from_numpy(np.concatenate(px)), torch.from_numpy(np.concatenate(pi))
 
+        def row_histogram(self, xyz, b, n_global):
+            gx, cpd = self._planes(xyz, b, n_global)
+            gy = _axis_index(xyz.numpy()[:, 1], b[2], b[3], cpd / (b[3] - b[2]), cpd)
+            return torch.from_numpy(np.bincount(gx * cpd + gy, minlength=cpd * cpd).astype(np.int64))
+
         def compute(self, xyz, ids, box, b, n_global, own, local, opts):
+            if len(own) == 4:  # row cuts: (lo_plane, lo_row, hi_plane, hi_row)
+                gx, cpd = self._planes(xyz, b, n_global)
+                gy = _axis_index(xyz.numpy()[:, 1], b[2], b[3], cpd / (b[3] - b[2]), cpd)
+                key = gx * cpd + gy
+                k0, k1 = own[0] * cpd + own[1], own[2] * cpd + own[3]
+                if not getattr(self, "planned", False):
+                    assert np.all((gx >= local[0]) & (gx < local[1])), "received a particle outside the local planes"
+                owned = (key >= k0) & (key < k1)
+                self.calls.append(dict(own=own, local=local, n=len(gx)))
+                need = 3  # pretend cells need 3 planes of halo beyond every plane the rank owns a row of
+                p0, p1 = own[0], -(-k1 // cpd)
+                flagged = (p0 > 0 and p0 - local[0] < need) or (p1 < cpd and local[1] - p1 < need)
+                batch = dict(ids=ids.numpy()[owned], recv_ids=ids.numpy(), bounds=np.array(b), own=own, local=local)
+                return batch, int(owned.sum()), flagged
             gx, _ = self._planes(xyz, b, n_global)
             if not getattr(self, "planned", False):  # (records laid out by a stale plan are garbage: the step is discarded and redone)
                 assert np.all((gx >= local[0]) & (gx < local[1])), "received a particle outside the local planes"
@@ -112,6 +131,7 @@ def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False):
     # ranks hold arbitrary (index-contiguous, spatially random) subsets of one global stream
     xyz = torch.from_numpy(gen.uniform(n_local, seed, start=start))
     be = RecordBackend() if records else NumpyBackend()
+    be.has_rows = rows
     res = D.compute_sharded(be, xyz, start, n_global, [0, 0, 0, 1, 1, 1], dist=dist, halo=1 if thin_halo else 4)
     if records:
         # the same particles again, with the plan: no planning collectives, same exchange, same result
@@ -130,6 +150,35 @@ def _worker(rank, world, port, n_global, seed, thin_halo, out, records=False):
              local=np.array(res.local), halo=res.halo, rounds=res.rounds, n_owned=res.n_owned, n_calls=len(be.calls))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_two_rank_row_cuts(tmp_path, gen):
+    """Slab cuts finer than a plane (rows of the x-major grid): the two ranks share a plane, each owns its rows of it, both
+    hold the whole plane plus the halo, every particle is owned exactly once and the split is balanced to a ROW's worth."""
+    import torch.multiprocessing as mp
+
+    D = importlib.import_module("the-tessellator_b200.distributed")
+    world, n, seed = 2, 20_000, 78
+    out = str(tmp_path / "rank{rank}.npz")
+    mp.spawn(_worker, args=(world, _free_port(), n, seed, False, out, True, True), nprocs=world, join=True)
+    pts = gen.uniform(n, seed)
+    cpd = D.cells_per_dimension(n)
+    b = np.array([pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max(), pts[:, 2].min(), pts[:, 2].max()])
+    gx = _axis_index(pts[:, 0], b[0], b[1], cpd / (b[1] - b[0]), cpd)
+    gy = _axis_index(pts[:, 1], b[2], b[3], cpd / (b[3] - b[2]), cpd)
+    key = gx * cpd + gy
+    r = [np.load(out.format(rank=k)) for k in range(world)]
+    k = [(int(o[0]) * cpd + int(o[1]), int(o[2]) * cpd + int(o[3])) for o in (r[0]["own"], r[1]["own"])]
+    assert k[0][0] == 0 and k[0][1] == k[1][0] and k[1][1] == cpd * cpd
+    assert k[0][1] % cpd != 0  # (with 20k random points the balanced cut does not fall on a plane boundary)
+    assert abs(int(r[0]["n_owned"]) - n // 2) <= np.bincount(key).max()
+    owned = np.concatenate([r[j]["ids"] for j in range(world)])
+    assert np.array_equal(np.sort(owned), np.arange(n))
+    for j in range(world):
+        assert np.all((key[r[j]["ids"]] >= k[j][0]) & (key[r[j]["ids"]] < k[j][1]))
+        lo, hi = r[j]["local"]
+        assert np.array_equal(np.sort(r[j]["recv_ids"]), np.nonzero((gx >= lo) & (gx < hi))[0])
+        assert lo == max(0, k[j][0] // cpd - 4) and hi == min(cpd, -(-k[j][1] // cpd) + 4)
 
 
 @pytest.mark.parametrize("records", [False, True])

@@ -492,6 +492,31 @@ def test_record_exchange_path_on_one_device(tess, gen):
     cpd = D.cells_per_dimension(n)
     cuts = D.slab_cuts(be.plane_histogram(xyz, b6, n).cpu().numpy(), 3)
     lo, hi = D.receive_ranges(cuts, 4)
+    owns = [(cuts[g], cuts[g + 1]) for g in range(3)]
+    # slab cuts finer than a plane: rows (x, y) of the x-major grid; two fake ranks then share a plane
+    rcuts = D.row_cuts(be.row_histogram(xyz, b6, n).cpu().numpy(), 3)
+    assert rcuts[0] == 0 and rcuts[-1] == cpd * cpd and any(c % cpd for c in rcuts[1:-1])
+    rlo, rhi = D.receive_ranges_rows(rcuts, cpd, 4)
+    rowns = [(rcuts[g] // cpd, rcuts[g] % cpd, rcuts[g + 1] // cpd, rcuts[g + 1] % cpd) for g in range(3)]
+    seen_rows = np.zeros(n, bool)
+    rc_counts, rrec, _ = be.pack_records(xyz, 0, b6, n, rlo, rhi)
+    rrec = rrec.clone()
+    o = 0
+    n_owned_rows = []
+    for g in range(3):
+        batch, n_owned, flag = be.compute_records(rrec[o:o + rc_counts[g]].contiguous(), BOX, b6, n, rowns[g], (rlo[g], rhi[g]), dict(outputs=7))
+        assert int(flag.item()) == 0
+        ids = batch.cell_ids
+        assert not seen_rows[ids].any()
+        seen_rows[ids] = True
+        n_owned_rows.append(n_owned)
+        assert np.array_equal(batch.volumes, wb.volumes[ids])
+        wfo = wb.face_offsets
+        for k in range(0, len(ids), 499):
+            i = ids[k]
+            assert np.array_equal(batch.cell_neighbors(k), wb.neighbors[wfo[i]:wfo[i + 1]]) and np.array_equal(batch.cell_areas(k), wb.areas[wfo[i]:wfo[i + 1]])
+        o += rc_counts[g]
+    assert seen_rows.all() and max(n_owned_rows) - min(n_owned_rows) < 200  # balanced to a row's worth, not a plane's (1.7k here)
     counts, rec, counts_dev = be.pack_records(xyz, 0, b6, n, lo, hi)
     assert counts == [int(v) for v in counts_dev.cpu().tolist()] and sum(counts) == rec.shape[0] > n
     rec = rec.clone()
@@ -504,7 +529,7 @@ def test_record_exchange_path_on_one_device(tess, gen):
         seg, seg2 = rec[o:o + counts[g]], rec2[o:o + counts[g]]
         ids1 = np.sort(seg[:, 3].contiguous().view(torch.int64).cpu().numpy())
         assert np.array_equal(ids1, np.sort(seg2[:, 3].contiguous().view(torch.int64).cpu().numpy()))
-        batch, n_owned, flag = be.compute_records(seg.contiguous(), BOX, b6, n, (cuts[g], cuts[g + 1]), (lo[g], hi[g]), dict(outputs=7))
+        batch, n_owned, flag = be.compute_records(seg.contiguous(), BOX, b6, n, owns[g], (lo[g], hi[g]), dict(outputs=7))
         assert int(flag.item()) == 0 and n_owned == batch.n_cells
         ids = batch.cell_ids
         seen[ids] = True

@@ -31,7 +31,7 @@ SYMBOLS = (
     "tess_result_areas", "tess_result_status", "tess_result_cell_ids", "tess_result_vertex_offsets", "tess_result_vertices",
     "tess_result_face_vertex_offsets", "tess_result_face_vertex_indices",
     "tess_result_counters", "tess_result_volume_sum", "tess_result_device_views",
-    "tess_plane_histogram", "tess_bounds", "tess_pack_for_slabs", "tess_pack_records", "tess_diagram_add_records_device",
+    "tess_plane_histogram", "tess_row_histogram", "tess_bounds", "tess_pack_for_slabs", "tess_pack_records", "tess_diagram_add_records_device",
     "tess_find_neighbors", "tess_find_cells_in_radius", "tess_search_create", "tess_search_expand", "tess_search_cursor", "tess_search_free", "tess_query_free", "tess_query_offsets", "tess_query_indices", "tess_query_status",
     "tess_result_download", "tess_set_main_tier", "tess_result_tier_stats", "tess_kernel_launch_count", "tess_measure_fp64_peak", "tess_result_timings", "tess_diagram_timings",
 )
@@ -61,6 +61,8 @@ class Slab(C.Structure):
         ("own_hi", C.c_uint32),
         ("local_lo", C.c_uint32),
         ("local_hi", C.c_uint32),
+        ("own_lo_row", C.c_uint32),
+        ("own_hi_row", C.c_uint32),
     ]
 
 
@@ -143,6 +145,7 @@ def lib() -> C.CDLL:
     sig("tess_diagram_timings", ci, vp, P(f64 * 1))
     sig("tess_measure_fp64_peak", ci, ci, P(f64))
     sig("tess_plane_histogram", ci, vp, sz, vp, u64, vp, vp)
+    sig("tess_row_histogram", ci, vp, sz, vp, u64, vp, vp)
     sig("tess_bounds", ci, vp, sz, vp, vp)
     sig("tess_pack_for_slabs", ci, vp, vp, i64, sz, vp, u64, ci, vp, vp, vp, vp, vp, sz, vp)
     sig("tess_pack_records", ci, vp, vp, i64, sz, vp, u64, ci, vp, vp, vp, vp, vp, vp, sz, vp)

@@ -392,6 +392,10 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
         g = spec_from_bounds(slab->bounds, slab->n_global);
         if (!(slab->local_lo <= slab->own_lo && slab->own_lo <= slab->own_hi && slab->own_hi <= slab->local_hi && slab->local_hi <= g.cpd))
             return fail(TESS_ERR_INVALID, "slab plane ranges must satisfy local_lo <= own_lo <= own_hi <= local_hi <= cpd");
+        if (slab->own_lo_row >= g.cpd || slab->own_hi_row >= g.cpd || (slab->own_hi_row > 0 && slab->own_hi >= slab->local_hi) ||
+            (slab->own_lo_row > 0 && slab->own_lo >= slab->local_hi) ||
+            (uint64_t)slab->own_lo * g.cpd + slab->own_lo_row > (uint64_t)slab->own_hi * g.cpd + slab->own_hi_row)
+            return fail(TESS_ERR_INVALID, "slab row offsets must be < cpd, lie in planes held locally, and keep the owned range non-negative");
         g.local_lo = slab->local_lo; g.local_hi = slab->local_hi; g.own_lo = slab->own_lo; g.own_hi = slab->own_hi;
         d->slab = true;
     } else {
@@ -452,7 +456,9 @@ static int initialize_impl(tess_diagram* d, const double* box, const tess_slab* 
     tr.mark("binning kernels");
     if (slab) {
         uint32_t b = 0, e = 0;
-        const size_t cb = static_cast<size_t>(g.own_lo - g.local_lo) * g.cpd * g.cpd, ce = static_cast<size_t>(g.own_hi - g.local_lo) * g.cpd * g.cpd;
+        // the owned cells: grid rows (x, y) in [own_lo*cpd + own_lo_row, own_hi*cpd + own_hi_row) — a run of the sorted order
+        const size_t cb = (static_cast<size_t>(g.own_lo - g.local_lo) * g.cpd + slab->own_lo_row) * g.cpd,
+                     ce = (static_cast<size_t>(g.own_hi - g.local_lo) * g.cpd + slab->own_hi_row) * g.cpd;
         TESS_CUDA_CHECK(cudaMemcpyAsync(&b, d->delim.as<uint32_t>() + cb, sizeof(b), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaMemcpyAsync(&e, d->delim.as<uint32_t>() + ce, sizeof(e), cudaMemcpyDeviceToHost, s));
         TESS_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1419,6 +1425,17 @@ int tess_plane_histogram(const double* xyz_dev, size_t n, const double bounds[6]
     const GridSpec g = spec_from_bounds(bounds, n_global);
     TESS_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * g.cpd, s));
     launch_plane_histogram(xyz_dev, n, g, reinterpret_cast<unsigned long long*>(counts_dev), s);
+    return TESS_OK;
+    TESS_CATCH
+}
+
+int tess_row_histogram(const double* xyz_dev, size_t n, const double bounds[6], uint64_t n_global, uint64_t* counts_dev, void* stream) {
+    if (!bounds || !counts_dev || (!xyz_dev && n)) return fail(TESS_ERR_INVALID, "NULL argument");
+    TESS_TRY
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GridSpec g = spec_from_bounds(bounds, n_global);
+    TESS_CUDA_CHECK(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * g.cpd * g.cpd, s));
+    launch_row_histogram(xyz_dev, n, g, reinterpret_cast<unsigned long long*>(counts_dev), s);
     return TESS_OK;
     TESS_CATCH
 }

@@ -143,6 +143,7 @@ size_t scan_tmp_bytes(size_t n);
 void launch_scatter_records(const double* xyz, const int64_t* ids, const uint32_t* cell_of, const uint32_t* rank_in_cell, const uint32_t* delim, Particle* arrived, uint32_t* arrived_idx, size_t n, cudaStream_t s);
 void launch_rank_fix(const Particle* arrived, const uint32_t* arrived_idx, const GridSpec& g, const uint32_t* delim, const uint64_t* groups, Particle* sorted, uint32_t* sorted_idx, uint64_t* groups_sorted, size_t n, cudaStream_t s);
 void launch_plane_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s);
+void launch_row_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s);
 void launch_pack_count(const double* xyz, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, unsigned long long* counts, cudaStream_t s);
 void launch_pack_scatter(const double* xyz, const int64_t* ids, int64_t id_base, size_t n, const GridSpec& g, int n_ranks, const uint32_t* lo_dev, const uint32_t* hi_dev, const unsigned long long* offsets, const unsigned long long* limits, unsigned long long* cursors, double* out_xyz, int64_t* out_ids, double* out_rec, cudaStream_t s);
 

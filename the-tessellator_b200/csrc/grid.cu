@@ -287,6 +287,16 @@ __global__ void __launch_bounds__(kThreads) rank_fix_kernel(const Particle* __re
 }
 
 // ---------------------------------------------------------------- slab helpers -------------
+__global__ void __launch_bounds__(kThreads) row_histogram_kernel(const double* __restrict__ xyz, size_t n, GridSpec g, unsigned long long* __restrict__ counts) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t key = 0xFFFFFFFFu;
+    if (valid) key = axis_index(xyz[3 * i], g.xmin, g.xmax, g.ix, g.cpd) * g.cpd + axis_index(xyz[3 * i + 1], g.ymin, g.ymax, g.iy, g.cpd);
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31;
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&counts[key], (unsigned long long)__popc(peers));
+}
+
 __global__ void __launch_bounds__(kThreads) plane_histogram_kernel(const double* __restrict__ xyz, size_t n, GridSpec g, unsigned long long* __restrict__ counts) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const bool valid = i < n;
@@ -407,6 +417,13 @@ void launch_rank_fix(const Particle* arrived, const uint32_t* arrived_idx, const
                      uint32_t* sorted_idx, uint64_t* groups_sorted, size_t n, cudaStream_t s) {
     if (!n) return;
     TESS_LAUNCH(rank_fix_kernel, blocks_for(n, kThreads), kThreads, 0, s, arrived, arrived_idx, g, delim, groups, sorted, sorted_idx, groups_sorted, n);
+    note_launch();
+    TESS_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_row_histogram(const double* xyz, size_t n, const GridSpec& g, unsigned long long* counts, cudaStream_t s) {
+    if (!n) return;
+    TESS_LAUNCH(row_histogram_kernel, blocks_for(n, kThreads), kThreads, 0, s, xyz, n, g, counts);
     note_launch();
     TESS_CUDA_CHECK(cudaGetLastError());
 }

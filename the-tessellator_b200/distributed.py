@@ -72,17 +72,32 @@ def receive_ranges(cuts: Sequence[int], halo: int) -> Tuple[List[int], List[int]
     return lo, hi
 
 
+def row_cuts(row_counts: np.ndarray, n_ranks: int) -> List[int]:
+    """Slab cuts finer than a plane: keys k = x*cpd + y of grid rows, c[0]=0 <= ... <= c[n_ranks]=cpd^2, every slab
+    [c[g], c[g+1]) holding about the same number of particles.  Cell ids are x-major (celery.rs:323-324), so a run of rows
+    is a run of the sorted order; whole planes hold 50 k cells at 10M points, rows 250."""
+    return slab_cuts(row_counts, n_ranks)
+
+
+def receive_ranges_rows(cuts: Sequence[int], cpd: int, halo: int) -> Tuple[List[int], List[int]]:
+    """Planes a rank must hold for row cuts: every plane it owns a row of, plus `halo` planes on each side."""
+    lo = [max(0, cuts[g] // cpd - halo) for g in range(len(cuts) - 1)]
+    hi = [min(cpd, -(-cuts[g + 1] // cpd) + halo) for g in range(len(cuts) - 1)]
+    return lo, hi
+
+
 @dataclass
 class SlabPlan:
     """What a step learns about an unchanged particle set (compute_sharded(plan=...))."""
 
     bounds6: np.ndarray
-    cuts: List[int]
+    cuts: List[int]          # plane indices, or grid-row keys x*cpd + y when `rows`
     halo: int
     send_counts: List[int]
     recv_counts: List[int]
     n_local: int
     n_global: int
+    rows: bool = False
 
 
 @dataclass
@@ -90,7 +105,7 @@ class SlabResult:
     """Per-rank outcome: rows are the owned cells in the rank's grid order."""
 
     batch: object            # CellBatch (or whatever the backend returns)
-    own: Tuple[int, int]
+    own: Tuple[int, ...]      # owned planes (lo, hi), or (lo_plane, lo_row, hi_plane, hi_row) with row cuts
     local: Tuple[int, int]
     n_owned: int
     halo: int
@@ -126,6 +141,12 @@ class SlabBackend:
         raise NotImplementedError
 
     has_records = False
+
+    # Optional: particles per grid row (x, y) -> tensor[cpd*cpd] int64; with it slabs are cut at row, not plane, granularity
+    def row_histogram(self, xyz, bounds6: np.ndarray, n_global: int):
+        raise NotImplementedError
+
+    has_rows = False
 
 
 class CudaSlabBackend(SlabBackend):
@@ -179,6 +200,14 @@ class CudaSlabBackend(SlabBackend):
             cap = sum(c) + 1024
 
     has_records = True
+    has_rows = True
+
+    def row_histogram(self, xyz, bounds6, n_global):
+        cpd = cells_per_dimension(n_global)
+        out = self._torch.empty(cpd * cpd, dtype=self._torch.int64, device=self.device)
+        b = np.ascontiguousarray(bounds6, dtype=np.float64)
+        self._lib.check(self._lib.lib().tess_row_histogram(xyz.data_ptr(), xyz.shape[0], b.ctypes.data, n_global, out.data_ptr(), self._stream()))
+        return out
 
     def pack_records(self, xyz, id_base, bounds6, n_global, lo, hi, planned_counts=None):
         torch = self._torch
@@ -295,20 +324,25 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
                 dist.all_reduce(mm, op=dist.ReduceOp.MAX)
                 b = torch.stack([-mm[:3], mm[3:]], dim=1).reshape(-1)
             bounds6 = b.cpu().numpy().astype(np.float64)
-        # ---- equal-count slab cuts from the per-plane histogram ----------------------------------
-        hist = backend.plane_histogram(xyz_local, bounds6, n_global)
+        # ---- equal-count slab cuts from the per-row (else per-plane) histogram ----------------------
+        rows = bool(getattr(backend, "has_rows", False)) and world > 1 and cpd >= 2
+        hist = backend.row_histogram(xyz_local, bounds6, n_global) if rows else backend.plane_histogram(xyz_local, bounds6, n_global)
         if multi:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        cuts = slab_cuts(hist.cpu().numpy(), world)
+        cuts = row_cuts(hist.cpu().numpy(), world) if rows else slab_cuts(hist.cpu().numpy(), world)
         mark("plan (bounds, histogram, cuts)")
     else:
-        bounds6, cuts, halo = plan.bounds6, plan.cuts, plan.halo
+        bounds6, cuts, halo, rows = plan.bounds6, plan.cuts, plan.halo, plan.rows
 
     rounds = 0
     while True:
         rounds += 1
-        lo, hi = receive_ranges(cuts, halo)
-        own = (cuts[rank], cuts[rank + 1])
+        if rows:
+            lo, hi = receive_ranges_rows(cuts, cpd, halo)
+            own = (cuts[rank] // cpd, cuts[rank] % cpd, cuts[rank + 1] // cpd, cuts[rank + 1] % cpd)  # (plane, row) .. (plane, row)
+        else:
+            lo, hi = receive_ranges(cuts, halo)
+            own = (cuts[rank], cuts[rank + 1])
         local = (lo[rank], hi[rank])
         mismatch = None
         if backend.has_records:
@@ -366,7 +400,8 @@ def compute_sharded(backend: SlabBackend, xyz_local, id_base: int, n_global: int
             return compute_sharded(backend, xyz_local, id_base, n_global, box, dist=dist, halo=halo, max_rounds=max_rounds, opts=opts, plan=None)
         done = (f & 1) == 0
         if done or rounds >= max_rounds or halo >= cpd:
-            new_plan = SlabPlan(bounds6=bounds6, cuts=list(cuts), halo=halo, send_counts=list(send_counts), recv_counts=list(recv_counts), n_local=n_local, n_global=n_global)
+            new_plan = SlabPlan(bounds6=bounds6, cuts=list(cuts), halo=halo, send_counts=list(send_counts), recv_counts=list(recv_counts), n_local=n_local, n_global=n_global,
+                                rows=rows)
             return SlabResult(batch=batch, own=own, local=local, n_owned=n_owned, halo=halo, n_received=n_received, rounds=rounds, plan=new_plan, halo_ok=done)
         halo = cpd if rounds + 1 >= max_rounds else min(cpd, 2 * halo)  # the last round takes every plane: it cannot be flagged
         plan = None

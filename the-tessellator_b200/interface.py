@@ -274,7 +274,12 @@ class Diagram:
         for i in range(6):
             s.bounds[i] = float(bounds[i])
         s.n_global = int(n_global)
-        s.own_lo, s.own_hi = int(own[0]), int(own[1])
+        # own = (lo_plane, hi_plane), or (lo_plane, lo_row, hi_plane, hi_row) for slab cuts finer than a plane
+        if len(own) == 4:
+            s.own_lo, s.own_lo_row, s.own_hi, s.own_hi_row = (int(v) for v in own)
+        else:
+            s.own_lo, s.own_hi = int(own[0]), int(own[1])
+            s.own_lo_row = s.own_hi_row = 0
         s.local_lo, s.local_hi = int(local[0]), int(local[1])
         check(_lib.lib().tess_diagram_initialize_slab(self._h, box.ctypes.data, C.byref(s), stream))
         self.initialized = True
