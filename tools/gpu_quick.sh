@@ -4,6 +4,6 @@ timeout 600 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_parity
 timeout 300 python bench.py --workload uniform1m --steps 3 --no-cpu-baseline 2>gpurun_out/b1.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('cells/s', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'clip ms', d['roofline']['avg_launch_ms'], 'fp64 frac', d['roofline_fp64']['frac'])
+print('cells/s', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'clip ms', d['roofline']['avg_launch_ms'], 'roofline', d['roofline']['bound'], d['roofline']['frac'])
 "
 tail -2 gpurun_out/b1.err
