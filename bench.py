@@ -394,8 +394,11 @@ def main():
                 bb = diagram.compute_all_cells_to_host(h_vol, h_off, h_nbr, h_area, h_stat, n_chunks=args.e2e_chunks, stream=stream, **opts)
             else:
                 stage.copy_(host_in, non_blocking=True)  # pinned host -> device
+                # (16 chunks when several GPUs share the host's memory bandwidth: the copies, not the clip kernel, are then the
+                # slower side, and nothing can be copied before the first chunk is computed — 8 GPUs, 10M points: 40.5 ms per
+                # step with 8 chunks, 35.1 ms with 16)
                 res = D.compute_sharded(backend, stage, start, n, BOX, dist=dist, halo=4, plan=state.get("plan"),
-                                        opts=dict(opts, host_sink=(h_vol, h_off, h_nbr, h_area, h_stat, args.e2e_chunks)))
+                                        opts=dict(opts, host_sink=(h_vol, h_off, h_nbr, h_area, h_stat, args.e2e_chunks or 16)))
                 state["plan"] = res.plan
                 bb = res.batch
             assert bb.n_faces <= cap_faces and bb.n_cells <= n_cells_local + 1024
@@ -413,7 +416,8 @@ def main():
             dist.all_reduce(bi)
         e2e = {"value": n / (e_ms * 1e-3), "unit": "cells/s", "ms_per_step": e_ms, "h2d_bytes_per_step": int(bi[0].item()), "d2h_bytes_per_step": int(bi[1].item()),
                "api": ("Diagram.add_particles(host) -> initialize -> compute_all_cells_to_host(pinned host arrays; %d chunks, copies overlap the clip kernel)" % (args.e2e_chunks or 8))
-               if world == 1 else "pinned host -> device copy -> compute_sharded(host_sink=pinned host arrays: each rank streams its rows while it clips)", "steps": e2e_steps}
+               if world == 1 else "pinned host -> device copy -> compute_sharded(host_sink=pinned host arrays, %d chunks: each rank streams its rows while it clips)" % (args.e2e_chunks or 16),
+               "steps": e2e_steps}
         if world == 1:  # the host copy carries the same volumes
             assert abs(float(h_vol[:hb.n_cells].sum().item()) - 1.0) < 1e-9
 

@@ -738,13 +738,15 @@ int compute_impl(const tess_diagram* d, const tess_opts* opts_in, const double* 
     const bool listed = streaming && P.row_of_slot != nullptr;  // rows in insertion order: a chunk of rows is a scattered set of slots
     const int C = streaming ? sink->n_chunks : 1;
     const uint64_t face_cap = sink ? sink->face_capacity : 0;
-    // Chunk sizes: equal at first, halving towards the end — the copies of the last two chunks are the
-    // only ones that no clip kernel hides, so those chunks are small.
+    // Chunk sizes: small at both ends.  When the clip kernel is the slower side (one GPU per host link: 184 ms of compute
+    // against 48 ms of copies at 10M cells) only the copy of the LAST chunk is exposed, so the chunks halve towards the end;
+    // when the copies are the slower side (8 GPUs sharing the host's memory bandwidth: 28 ms of copies against 22 ms of
+    // compute) nothing can be copied before the FIRST chunk is computed, so the chunks also grow from a small first one.
     std::vector<size_t> chunk_row(C + 1, 0);
     {
         std::vector<unsigned long long> w(C);
         unsigned long long sum = 0;
-        for (int c = 0; c < C; ++c) sum += (w[c] = 1ull << std::min(C - 1 - c, 4));
+        for (int c = 0; c < C; ++c) sum += (w[c] = 1ull << std::min(std::min(C - 1 - c, c + 2), 4));
         unsigned long long acc = 0;
         for (int c = 0; c < C; ++c) {
             acc += w[c];
