@@ -101,7 +101,10 @@ struct __align__(16) ThreadShared {
     uint32_t cell[32 * ThreadCfg::WARPS];           // consumer -> producer: sorted slot of the cell under construction / C_IDLE / C_EXIT
 };
 static_assert(sizeof(ThreadShared) <= 232448, "tables and rings must fit the 227 KB of one SM");
-#ifdef TESS_T_STATS  // development build: phase / participation statistics of the state machines (printed after the launch)
+#ifdef TESS_T_STATS  // development build: phase / participation statistics of the state machines (printed after the launch).
+// Counters: 0 consumer rounds; 1/2 cut phases / lanes in them; 3/4 classify phases / lanes; 5/6 result phases / lanes; 7 idle
+// sleeps; 11 ring items consumed; 13-16 producer steps / items / candidates looked at / ring room; 17/18 producer polls / with
+// work; 19 producer step cycles; 21-23 consumer cycles in classify / cut / results; 24 consumer warp cycles.
 __device__ unsigned long long g_tstats[32];
 #define TCLK() clock64()
 #define TSTAT(i, v) atomicAdd(&g_tstats[i], (unsigned long long)(v))
@@ -728,41 +731,41 @@ __global__ void __launch_bounds__(32 * (ThreadCfg::WARPS + ThreadCfg::PWARPS), 1
                 }
             }
             if (state == S_TEST) {
-            {
-                // Plane::halfway_from_origin_to (vector3.rs:223-225); mag_sq(rel) is r2
-                const double m = __dsqrt_rn(r2);
-                const double inv = __ddiv_rn(1.0, m);
-                pl.nx = mul(rx, inv); pl.ny = mul(ry, inv); pl.nz = mul(rz, inv);
-                pl.off = dot3(pl.nx, pl.ny, pl.nz, mul(rx, 0.5), mul(ry, 0.5), mul(rz, 0.5));
-            }
-            uint32_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
-            const int top = 64 - __clzll((long long)M.vlive);  // slots above the highest live one are not read
-#pragma unroll
-            for (int j = 0; j < ThreadCfg::V; ++j) {
-                if ((j & 3) == 0 && j >= top) break;
-                const double sd = signed_distance(pl, M.t->vx[j][lane], M.t->vy[j][lane], M.t->vz[j][lane]);
-                if (j < 32) {
-                    if (sd < -TESS_TOL) in_lo |= 1u << j;   // vector3.rs:173
-                    if (sd > TESS_TOL) out_lo |= 1u << j;   // vector3.rs:171
-                } else {
-                    if (sd < -TESS_TOL) in_hi |= 1u << (j - 32);
-                    if (sd > TESS_TOL) out_hi |= 1u << (j - 32);
+                {
+                    // Plane::halfway_from_origin_to (vector3.rs:223-225); mag_sq(rel) is r2
+                    const double m = __dsqrt_rn(r2);
+                    const double inv = __ddiv_rn(1.0, m);
+                    pl.nx = mul(rx, inv); pl.ny = mul(ry, inv); pl.nz = mul(rz, inv);
+                    pl.off = dot3(pl.nx, pl.ny, pl.nz, mul(rx, 0.5), mul(ry, 0.5), mul(rz, 0.5));
                 }
-            }
-            in = (((unsigned long long)in_hi << 32) | in_lo) & M.vlive;  // dead slots hold stale coordinates
-            out = (((unsigned long long)out_hi << 32) | out_lo) & M.vlive;
-            if (out == 0ull) {
-                state = S_FETCH;  // polyhedron.rs:408-410: no cut
-            } else if ((M.vlive & ~in & ~out) != 0ull) {
-                // a vertex ON the plane: the reference destroys it and re-creates it as a copy (polyhedron.rs:555-565),
-                // after which vertices are no longer 3-valent — the warp-per-cell kernel's serial walk does that
-                status |= ST_TABLE_EXHAUSTED;
-                failed = true;
-                st_volatile_f64(&S->thr[c], -2.0);
-                state = S_FETCH;  // drains the ring up to the end marker
-            } else {
-                state = S_CUT;
-            }
+                uint32_t in_lo = 0, in_hi = 0, out_lo = 0, out_hi = 0;
+                const int top = 64 - __clzll((long long)M.vlive);  // slots above the highest live one are not read
+#pragma unroll
+                for (int j = 0; j < ThreadCfg::V; ++j) {
+                    if ((j & 3) == 0 && j >= top) break;
+                    const double sd = signed_distance(pl, M.t->vx[j][lane], M.t->vy[j][lane], M.t->vz[j][lane]);
+                    if (j < 32) {
+                        if (sd < -TESS_TOL) in_lo |= 1u << j;   // vector3.rs:173
+                        if (sd > TESS_TOL) out_lo |= 1u << j;   // vector3.rs:171
+                    } else {
+                        if (sd < -TESS_TOL) in_hi |= 1u << (j - 32);
+                        if (sd > TESS_TOL) out_hi |= 1u << (j - 32);
+                    }
+                }
+                in = (((unsigned long long)in_hi << 32) | in_lo) & M.vlive;  // dead slots hold stale coordinates
+                out = (((unsigned long long)out_hi << 32) | out_lo) & M.vlive;
+                if (out == 0ull) {
+                    state = S_FETCH;  // polyhedron.rs:408-410: no cut
+                } else if ((M.vlive & ~in & ~out) != 0ull) {
+                    // a vertex ON the plane: the reference destroys it and re-creates it as a copy (polyhedron.rs:555-565),
+                    // after which vertices are no longer 3-valent — the warp-per-cell kernel's serial walk does that
+                    status |= ST_TABLE_EXHAUSTED;
+                    failed = true;
+                    st_volatile_f64(&S->thr[c], -2.0);
+                    state = S_FETCH;  // drains the ring up to the end marker
+                } else {
+                    state = S_CUT;
+                }
             }
         }
 
