@@ -7,20 +7,24 @@
 //   Polyhedron::{weighted_normal, compute_volume, compute_neighbors}   polyhedron.rs:776-881
 //   VoronoiFace::compute_area                             interface.rs:408-410
 //
-// Design (DESIGN.md §clip):
-//   * the polyhedron is a half-edge mesh held in SHARED MEMORY (fixed-capacity tables with
-//     bitmask allocators) instead of pool.rs's heap pools; one half-edge = one 32-bit word
-//     {next, flip, target, face} of 8-bit slot ids (16-bit ids in the large-cell variant);
-//   * candidates are staged 32 at a time: one lane per search-table entry reads the grid
-//     delimiters, a warp scan flattens the per-cell ranges, then one lane per candidate loads its
-//     32-byte particle record, evaluates |r|^2 and builds its bisector plane in parallel;
-//   * plane-side classification is one lane per vertex + warp ballots; the start edge is found by
-//     a lane-per-half-edge ballot; the boundary walk itself is warp-uniform;
-//   * dead vertices/edges/faces are retired by ballots over the tables (no recursion);
-//   * arithmetic is the reference's, operation for operation (tess_math.cuh), so vertex
-//     coordinates — and therefore every Inside/Incident/Outside decision — are bit-identical to
-//     the CPU oracle's.  Slot numbering differs from pool.rs's LIFO order; that only permutes the
-//     order in which faces are listed.
+// Design (DESIGN.md §4):
+//   * the polyhedron is a half-edge mesh held in SHARED MEMORY (fixed-capacity tables) instead of pool.rs's heap
+//     pools; one half-edge = one 32-bit word {next, flip, target, face} of 8-bit slot ids (64-bit words of 16-bit ids
+//     in the medium / large configurations).  Half-edge and face slots are handed out and recycled in pool.rs's LIFO
+//     order (free stacks in shared memory), so slot numbers — and with them find_outgoing_edge's "first edge in slot
+//     order", every face's starting edge, the face order, the fan anchors and the summation orders — are the
+//     reference's: volumes, areas and the neighbour order come out bit-identical to the CPU oracle;
+//   * candidates are staged 32 at a time: one lane per search-table entry reads the grid delimiters, a warp scan
+//     flattens the per-cell ranges, then one lane per candidate loads its 32-byte particle record, evaluates |r|^2
+//     and builds its bisector plane in parallel; a tile with enough planes waiting is screened lane-per-plane first;
+//   * plane-side classification is one lane per vertex + warp ballots;
+//   * the cut is lane-parallel when no vertex lies on the plane (cut_parallel: one lane per half-edge leaving an
+//     Outside vertex, crossings linked into the reference's walk order by list ranking) and the reference-shaped
+//     serial walk, warp-uniform, otherwise; the main pass is the instantiation WITHOUT the walk (SERIAL = false):
+//     cells that need it are handed back and finished by the instantiation that has it;
+//   * one warp per CTA in the small configuration: the tables sit at the CTA's shared-memory base, a constant;
+//   * arithmetic is the reference's, operation for operation (tess_math.cuh, no FMA contraction), so vertex
+//     coordinates — and therefore every Inside/Incident/Outside decision — are bit-identical to the CPU oracle's;
 //   * NEW vs the reference: the shell walk stops at the first table entry whose key exceeds
 //     4*max|v|^2 and skips candidates with |r|^2 >= 4*max|v|^2.  Such candidates cannot have a
 //     vertex Outside (n.v - |r|/2 <= |v| - |r|/2 <= 0 < tol), i.e. find_outgoing_edge
