@@ -34,6 +34,10 @@ struct emu_query_args {
     uint64_t cap;
     uint32_t* flags;    // n_query
     uint32_t os_threads, reverse;
+    // mode 4 (ExpandingSearch::expand): cursors in / out (n_query each), cells_to_add
+    const uint64_t* cursor_in;
+    uint64_t* cursor_out;
+    uint64_t cells_to_add;
 };
 
 int emu_query_run(emu_query_args* a) {
@@ -69,6 +73,9 @@ int emu_query_run(emu_query_args* a) {
     Q.radius = a->radius;
     Q.mode = a->mode;
     Q.target_group = a->target_group;
+    Q.cursor_in = a->cursor_in;
+    Q.cursor_out = a->cursor_out;
+    Q.cells_to_add = a->cells_to_add;
     std::vector<uint32_t> counts(a->n_query + 1, 0u);
     Q.counts = counts.data();
     Q.flags = a->flags;

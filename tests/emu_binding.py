@@ -178,6 +178,7 @@ class QueryArgs(C.Structure):
         ("table_len", C.c_uint32), ("table_full", C.c_uint32), ("bounds", C.c_double * 6), ("cell_info", C.c_double * 6), ("cpd", C.c_uint32),
         ("xyz", C.c_void_p), ("n_query", C.c_uint32), ("radius", C.c_double), ("mode", C.c_int32), ("target_group", C.c_int64),
         ("offsets", C.c_void_p), ("indices", C.c_void_p), ("cap", C.c_uint64), ("flags", C.c_void_p), ("os_threads", C.c_uint32), ("reverse", C.c_uint32),
+        ("cursor_in", C.c_void_p), ("cursor_out", C.c_void_p), ("cells_to_add", C.c_uint64),
     ]
 
 
@@ -217,9 +218,10 @@ def binning(points, oracle: "ob.Diagram", ids=None, groups=None, local=None, os_
     return out
 
 
-def radius_query(grid: EmuGrid, xyz, radius, mode, target_group=-1, os_threads=4, reverse=False):
+def radius_query(grid: EmuGrid, xyz, radius, mode, target_group=-1, os_threads=4, reverse=False, cursors=None, cells_to_add=0):
     """query.cu on the emulator: per query the particle ids in the reference's order.  mode 0 cell radius, 1 real radius,
-    2 expand_all_in_radius (search table)."""
+    2 expand_all_in_radius (search table), 3 find_cells_in_radius (grid cell ids), 4 ExpandingSearch::expand from `cursors`
+    (returns the new cursors as a third value)."""
     L = _aux_lib("query")
     q = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
     m = q.shape[0]
@@ -233,9 +235,14 @@ def radius_query(grid: EmuGrid, xyz, radius, mode, target_group=-1, os_threads=4
     a.xyz, a.n_query, a.radius, a.mode, a.target_group = q.ctypes.data, m, radius, mode, target_group
     a.offsets, a.indices, a.cap, a.flags = offsets.ctypes.data, indices.ctypes.data, cap, flags.ctypes.data
     a.os_threads, a.reverse = os_threads, int(reverse)
+    cin = cout = None
+    if mode == 4:
+        cin, cout = np.ascontiguousarray(cursors, np.uint64), np.zeros(m, np.uint64)
+        a.cursor_in, a.cursor_out, a.cells_to_add = cin.ctypes.data, cout.ctypes.data, min(int(cells_to_add), 2 ** 64 - 1)
     assert L.emu_query_run(C.byref(a)) == 0
     o = offsets.astype(np.int64)
-    return [indices[o[i]:o[i + 1]].tolist() for i in range(m)], flags
+    lists = [indices[o[i]:o[i + 1]].tolist() for i in range(m)]
+    return (lists, flags, cout) if mode == 4 else (lists, flags)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -188,3 +188,42 @@ def test_chunk_work_lists_volume_sum_and_gathers(eb, gen):
     st = np.full(1000, 0x80000005, np.uint32)
     L.emu_clear_status_bits(st.ctypes.data, 1000, 0x80000000)
     assert np.all(st == 5)
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_expand_cursor_and_cells_in_radius_on_the_emulator(eb, gen, reverse):
+    """query.cu modes 3 (Celery::find_cells_in_radius, celery.rs:753-797) and 4 (ExpandingSearch::expand with a cursor,
+    celery.rs:907-963) on the emulated kernel: uneven steps from saved cursors, a truncated table that runs out under the
+    cursor (flagged, cursor left at the table's end), all against the oracle — lists, order and cursors."""
+    pts = gen.uniform(3000, 93)
+    g = eb.EmuGrid(pts, (0, 0, 0, 1, 1, 1), table_radius=-1)
+    od = g.oracle
+    sx = g.cell_info[0]
+    qs = np.concatenate([gen.uniform(10, 94), [[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]]])
+    for r in (0.0, 0.7 * sx, 2.6 * sx):
+        cells = eb.radius_query(g, qs, r, 3, reverse=reverse)[0]
+        for i, q in enumerate(qs):
+            assert cells[i] == od.find_cells_in_radius(*q, r)
+    oes = [od.expanding_search(*q) for q in qs]
+    cur = np.zeros(len(qs), np.uint64)
+    for radius, cells_to_add in (((1.5 * sx) ** 2, 1), ((1.5 * sx) ** 2, 5), ((1.5 * sx) ** 2, 1000), ((4 * sx) ** 2, 37), (float("inf"), 400)):
+        got, flags, cur = eb.radius_query(g, qs, radius, 4, cursors=cur, cells_to_add=cells_to_add, reverse=reverse)
+        assert not flags.any()
+        for i in range(len(qs)):
+            assert got[i] == oes[i].expand(radius, cells_to_add), (radius, cells_to_add, i)
+    # the celery.rs:1343-1404 walk, one table entry per call
+    g2 = eb.EmuGrid(gen.uniform(100, 24), (0, 0, 0, 1, 1, 1), table_radius=-1)
+    assert g2.cpd == 5 and g2.table_key.size == 729
+    cur, seen = np.zeros(1, np.uint64), []
+    for step in range(729):
+        got, _, cur = eb.radius_query(g2, [[0.5, 0.5, 0.5]], 10.0, 4, cursors=cur, cells_to_add=1, reverse=reverse)
+        seen += got[0]
+        assert int(cur[0]) == step + 1
+    assert len(seen) == 100 and len(set(seen)) == 100
+    assert eb.radius_query(g2, [[0.5, 0.5, 0.5]], 10.0, 4, cursors=cur, cells_to_add=50)[0][0] == []
+    # a truncated table under the cursor
+    g3 = eb.EmuGrid(pts, (0, 0, 0, 1, 1, 1), table_radius=2)
+    got, flags, cur = eb.radius_query(g3, qs[:3], float("inf"), 4, cursors=np.zeros(3, np.uint64), cells_to_add=10 ** 6, reverse=reverse)
+    assert np.all(flags == 2) and np.all(cur == g3.table_key.size)  # TABLE_EXHAUSTED: the host widens the table and asks again
+    for i in range(3):
+        assert got[i] == od.expanding_search(*qs[i]).expand(float("inf"), g3.table_key.size)

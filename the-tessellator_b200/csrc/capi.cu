@@ -1318,7 +1318,7 @@ static int run_query(const tess_diagram* d, const double* xyz, size_t m, double 
         if (mode != 4 || Q.table_full) break;
         bool ran_off = false;
         for (size_t i = 0; i < m; ++i) ran_off |= (q->status[i] & ST_TABLE_EXHAUSTED) != 0;
-        if (!ran_off) break;
+        if (!ran_off || R >= static_cast<int>(d->grid.cpd)) break;  // (a table of half-width cpd is the full table)
         R = std::min(2 * R, static_cast<int>(d->grid.cpd));
     }
     const uint64_t total = q->offsets[m];
