@@ -14,14 +14,14 @@ fn main() {
         .args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"])
         .args(&["-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
-        .args(["capi.cu", "grid.cu", "clip.cu", "outputs.cu", "query.cu"].iter().map(|f| csrc.join(f)))
+        .args(["capi.cu", "grid.cu", "clip.cu", "clip_thread.cu", "outputs.cu", "query.cu"].iter().map(|f| csrc.join(f)))
         .arg("-lcudart")
         .status()
         .expect("nvcc not found: the-tessellator-b200 has no CPU fallback");
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=tess_b200");
-    for f in &["capi.cu", "grid.cu", "clip.cu", "outputs.cu", "query.cu", "common.cuh", "tess_math.cuh"] {
+    for f in &["capi.cu", "grid.cu", "clip.cu", "clip_thread.cu", "outputs.cu", "query.cu", "common.cuh", "cube_tables.cuh", "tess_math.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include").join("tess.h").display());

@@ -175,3 +175,16 @@ def test_rust_repr_c_structs_match_the_header():
         rbody = re.search(r"#\[repr\(C\)\]\s*(?:#\[derive\([^)]*\)\]\s*)?pub struct %s \{(.*?)\}" % name, ffi, flags=re.S).group(1)
         r_fields = [(m.group(1), m.group(2).strip()) for m in re.finditer(r"pub ([a-z_0-9]+): ([^,]+),", rbody)]
         assert r_fields == c_fields, (name, r_fields, c_fields)
+
+
+def test_rust_build_script_compiles_the_makefiles_sources():
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "the-tessellator_b200", "csrc", "Makefile")).read()
+    srcs = re.search(r"^SRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()
+    rs = open(os.path.join(root, "rust", "build.rs")).read()
+    listed = re.findall(r'"([a-z_]+\.cu)"', rs.split(".arg(\"-lcudart\")")[0])
+    assert sorted(listed) == sorted(srcs), (listed, srcs)
+    for flag in ("-fmad=false", "-prec-div=true", "-prec-sqrt=true", "arch=compute_100a,code=sm_100a"):
+        assert flag in rs and flag in mk
