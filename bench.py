@@ -124,10 +124,10 @@ def load_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_traffic_per_launch():
+def ncu_traffic_per_launch(path=None):
     """DRAM bytes and warp instructions per clip-kernel launch from the committed ncu capture (profiles/clip_kernel_traffic.json,
     written by profiles/make_traffic_json.py).  The file carries a hash of the kernel sources: a capture of other code is refused."""
-    p = os.path.join(ROOT, "profiles", "clip_kernel_traffic.json")
+    p = path or os.path.join(ROOT, "profiles", "clip_kernel_traffic.json")
     if not os.path.exists(p):
         return None
     try:

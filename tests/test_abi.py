@@ -3,6 +3,7 @@ what include/tess.h declares, and the product refuses to compute without a devic
 import ctypes
 import importlib
 import os
+import sys
 import re
 import subprocess
 
@@ -188,3 +189,26 @@ def test_rust_build_script_compiles_the_makefiles_sources():
     assert sorted(listed) == sorted(srcs), (listed, srcs)
     for flag in ("-fmad=false", "-prec-div=true", "-prec-sqrt=true", "arch=compute_100a,code=sm_100a"):
         assert flag in rs and flag in mk
+
+
+def test_bench_refuses_an_ncu_capture_of_other_kernel_sources(tmp_path):
+    """bench.py's `roofline` takes the instruction count per cell from profiles/clip_kernel_traffic.json, which carries a
+    SHA-256 of the kernel sources it was captured from: a file whose hash does not match the sources is not used."""
+    import importlib.util
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sys.path.insert(0, os.path.join(root, "profiles"))
+    from make_traffic_json import kernel_sources_sha256
+
+    good = dict(warp_instructions_per_launch=1.8e11, cells_per_launch=10_000_000, dram_bytes_per_launch=6.2e9, issue_active_pct=85.8,
+                kernel_sources_sha256=kernel_sources_sha256())
+    pg, pb = tmp_path / "good.json", tmp_path / "bad.json"
+    json.dump(good, open(pg, "w"))
+    json.dump(dict(good, kernel_sources_sha256="0" * 64), open(pb, "w"))
+    assert bench.ncu_traffic_per_launch(str(pg))["cells_per_launch"] == 10_000_000
+    assert bench.ncu_traffic_per_launch(str(pb)) is None
+    assert bench.ncu_traffic_per_launch(str(tmp_path / "missing.json")) is None
