@@ -236,3 +236,27 @@ def test_slab_cuts_and_ranges():
     # fewer planes than ranks: empty slabs are allowed, the cuts stay monotone
     c = D.slab_cuts(np.array([5, 5]), 4)
     assert c[0] == 0 and c[-1] == 2 and c == sorted(c)
+
+
+def test_row_cuts_and_ranges():
+    """Slab cuts at grid-row granularity: keys x*cpd + y; the planes a rank must hold are every plane it owns a row of plus
+    the halo; whole-plane cuts are the special case own_*_row == 0."""
+    D = importlib.import_module("the-tessellator_b200.distributed")
+    cpd = 10
+    rows = np.full(cpd * cpd, 7, dtype=np.int64)
+    c = D.row_cuts(rows, 8)
+    assert c[0] == 0 and c[-1] == cpd * cpd and c == sorted(c)
+    loads = [int(rows[c[g]:c[g + 1]].sum()) for g in range(8)]
+    assert max(loads) - min(loads) <= 7  # balanced to one row's worth (plane cuts: 10 rows' worth)
+    lo, hi = D.receive_ranges_rows(c, cpd, 2)
+    for g in range(8):
+        first_plane, last_plane = c[g] // cpd, (c[g + 1] - 1) // cpd
+        assert lo[g] == max(0, first_plane - 2) and hi[g] == min(cpd, last_plane + 1 + 2)
+    # a cut on a plane boundary needs no extra plane
+    lo, hi = D.receive_ranges_rows([0, 50, 100], cpd, 1)
+    assert lo == [0, 4] and hi == [6, 10]
+    # an uneven histogram: the cut follows the mass
+    rows = np.ones(cpd * cpd, dtype=np.int64)
+    rows[33] = 1000
+    c = D.row_cuts(rows, 2)
+    assert c[1] in (33, 34)
